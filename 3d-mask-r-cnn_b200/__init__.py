@@ -1,0 +1,30 @@
+"""3d-mask-r-cnn_b200 -- B200-native (sm_100a) ROI hot path of 3D Mask R-CNN.
+
+Scope: NonMaxSuppression3D and CropAndResize3D forward /
+grad-image / grad-boxes behind the reference's own custom-op surface
+(core/custom_op/custom_op.py).  Layout:
+
+    csrc/        hand-written CUDA kernels + the C ABI (include/roi3d.h)
+    lib/         libroi3d_b200.so, built in-tree by _lib.build()
+    custom_op.py host-side mirror of the reference's four callables + gradient
+    tf_ops/      TensorFlow op registration sources for the real drop-in
+
+The directory name is not a Python identifier; import it through the
+``roi3d_b200`` shim at the repository root (``import roi3d_b200``).
+Importing fails loudly when the CUDA library has not been built: there is no
+CPU fallback on this path.
+"""
+from . import _lib
+
+_lib.load()                     # ImportError if libroi3d_b200.so is missing
+
+from . import custom_op         # noqa: E402
+from .custom_op import (        # noqa: E402,F401
+    InvalidArgumentError,
+    crop_and_resize_3d,
+    crop_and_resize_3d_grad_boxes,
+    crop_and_resize_3d_grad_image,
+    non_max_suppression_3d,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,133 @@
+// roi3d_abi.cu -- the C ABI of libroi3d_b200.so (see include/roi3d.h): argument
+// validation, variant selection and kernel launches.  No torch / TF types, no
+// allocation, no device or stream synchronisation, no CPU fallback.
+#include "roi3d_common.cuh"
+#include <atomic>
+#include <string.h>
+
+namespace roi3d {
+thread_local int g_last_cuda_error = 0;
+thread_local long long g_launches = 0;
+static std::atomic<int> g_options[OPT_COUNT];
+int option_value(int which) { return g_options[which].load(std::memory_order_relaxed); }
+
+static int option_index(const char *name) {
+    if (!name) return -1;
+    if (!strcmp(name, "car_fwd_variant")) return OPT_CAR_FWD_VARIANT;
+    if (!strcmp(name, "car_bwd_variant")) return OPT_CAR_BWD_VARIANT;
+    if (!strcmp(name, "nms_variant")) return OPT_NMS_VARIANT;
+    return -1;
+}
+
+static bool geom_ok(const CarGeom &g) {
+    return g.B > 0 && g.H > 0 && g.W > 0 && g.D > 0 && g.C > 0 && g.n >= 0 && g.ph > 0 && g.pw > 0 && g.pd > 0;
+}
+// the kernels index one batch item with 32-bit element offsets and per-axis tables of <= 64 samples
+static bool geom_supported(const CarGeom &g) {
+    const long long per_image = (long long)g.H * g.W * g.D * g.C;
+    return per_image < (1ll << 31);
+}
+}  // namespace roi3d
+
+using namespace roi3d;
+
+extern "C" {
+
+const char *roi3d_version(void) { return "roi3d-b200 0.1.0 (sm_100a)"; }
+
+const char *roi3d_strerror(int code) {
+    switch (code) {
+    case ROI3D_OK: return "ok";
+    case ROI3D_EINVAL: return "invalid argument";
+    case ROI3D_EWORKSPACE: return "workspace missing, too small or misaligned";
+    case ROI3D_EUNSUPPORTED: return "shape not supported by the sm_100a kernels";
+    case ROI3D_ECUDA: return "CUDA error (see roi3d_last_cuda_error)";
+    default: return "unknown roi3d error";
+    }
+}
+
+int roi3d_last_cuda_error(void) { return g_last_cuda_error; }
+long long roi3d_kernel_launches(void) { return g_launches; }
+void roi3d_reset_kernel_launches(void) { g_launches = 0; }
+
+int roi3d_set_option(const char *name, int value) {
+    const int i = option_index(name);
+    if (i < 0) return ROI3D_EINVAL;
+    g_options[i].store(value, std::memory_order_relaxed);
+    return ROI3D_OK;
+}
+int roi3d_get_option(const char *name, int *value) {
+    const int i = option_index(name);
+    if (i < 0 || !value) return ROI3D_EINVAL;
+    *value = g_options[i].load(std::memory_order_relaxed);
+    return ROI3D_OK;
+}
+
+size_t roi3d_nms3d_workspace_bytes(int n) { return nms3d_workspace_bytes(n); }
+
+int roi3d_nms3d(const float *boxes, const float *scores, int n, int max_out, float iou_thr,
+                int *keep_idx, int *keep_count, void *workspace, size_t workspace_bytes,
+                roi3d_stream_t stream)
+{
+    if (n < 0 || max_out < 0 || !keep_count) return ROI3D_EINVAL;
+    if (!(iou_thr >= 0.0f && iou_thr <= 1.0f)) return ROI3D_EINVAL;       // "iou_threshold must be in [0, 1]"
+    if (n > 0 && max_out > 0 && (!boxes || !scores || !keep_idx)) return ROI3D_EINVAL;
+    return launch_nms3d(boxes, scores, n, max_out, iou_thr, keep_idx, keep_count, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
+                    const float *boxes, const int *box_index, int n,
+                    int ph, int pw, int pd, int method, float extrapolation_value,
+                    float *crops, roi3d_stream_t stream)
+{
+    const CarGeom g{B, H, W, D, C, n, ph, pw, pd};
+    if (!geom_ok(g)) return ROI3D_EINVAL;
+    if (method != ROI3D_METHOD_TRILINEAR && method != ROI3D_METHOD_NEAREST) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!image || !boxes || !box_index || !crops) return ROI3D_EINVAL;
+    if (!geom_supported(g)) return ROI3D_EUNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int variant = option_value(OPT_CAR_FWD_VARIANT);
+    const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
+                          ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(crops)) & 15) == 0;
+    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
+    if (variant == 2 && plane_ok) return launch_car3d_fwd_plane(image, boxes, box_index, g, extrapolation_value, crops, s);
+    return launch_car3d_fwd_direct(image, boxes, box_index, g, method, extrapolation_value, crops, s);
+}
+
+int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *box_ind, int n,
+                           int ph, int pw, int pd, int B, int H, int W, int D, int C, int method,
+                           float *grad_image, roi3d_stream_t stream)
+{
+    const CarGeom g{B, H, W, D, C, n, ph, pw, pd};
+    if (!geom_ok(g)) return ROI3D_EINVAL;
+    if (method != ROI3D_METHOD_TRILINEAR && method != ROI3D_METHOD_NEAREST) return ROI3D_EINVAL;
+    if (!grad_image) return ROI3D_EINVAL;
+    if (!geom_supported(g)) return ROI3D_EUNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the op's contract: the whole output is defined (GI.so@0x3ec5 zero-fills it)
+    ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
+    if (n == 0) return ROI3D_OK;
+    if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;
+    int variant = option_value(OPT_CAR_BWD_VARIANT);
+    const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
+                          ((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(grad_image)) & 15) == 0;
+    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
+    if (variant == 2 && plane_ok) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s);
+    return launch_car3d_grad_image_direct(grads, boxes, box_ind, g, method, grad_image, s);
+}
+
+int roi3d_car3d_grad_boxes(const float *grads, const float *image, int B, int H, int W, int D, int C,
+                           const float *boxes, const int *box_ind, int n, int ph, int pw, int pd,
+                           float *grad_boxes, roi3d_stream_t stream)
+{
+    const CarGeom g{B, H, W, D, C, n, ph, pw, pd};
+    if (!geom_ok(g)) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!grads || !image || !boxes || !box_ind || !grad_boxes) return ROI3D_EINVAL;
+    if (!geom_supported(g)) return ROI3D_EUNSUPPORTED;
+    return launch_car3d_grad_boxes(grads, image, boxes, box_ind, g, grad_boxes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

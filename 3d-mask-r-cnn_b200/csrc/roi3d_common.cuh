@@ -1,0 +1,99 @@
+// roi3d_common.cuh -- shared device helpers for the ROI hot-path kernels (sm_100a).
+//
+// Arithmetic contract: the reference's kernels are scalar SSE code with one
+// rounding per fp32 operation (no FMA).  Every helper here that feeds a
+// bit-exact comparison (sample coordinates, IoU, the forward lerps) spells the
+// operations with __f*_rn intrinsics so nvcc can neither contract them into
+// FMAs nor reassociate them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/roi3d.h"
+
+namespace roi3d {
+
+// ---- host-side bookkeeping ------------------------------------------------
+extern thread_local int g_last_cuda_error;
+extern thread_local long long g_launches;
+int option_value(int which);
+enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_COUNT };
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return ROI3D_ECUDA;
+}
+#define ROI3D_CUDA_TRY(expr)                                        \
+    do {                                                            \
+        cudaError_t e__ = (expr);                                   \
+        if (e__ != cudaSuccess) return ::roi3d::cuda_fail(e__);     \
+    } while (0)
+#define ROI3D_LAUNCH_CHECK()                                        \
+    do {                                                            \
+        ++::roi3d::g_launches;                                      \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return ::roi3d::cuda_fail(e__);     \
+    } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- sample coordinates (CAR.so@0x499a-0x4ae5, 0x533a) ---------------------
+// scale = ((a2 - a1) * f(dim-1)) / f(p-1)            (p > 1), else 0
+// in(k) = a1 * f(dim-1) + f(k) * scale               (p > 1)
+//       = float(double(a1 + a2) * 0.5 * double(dim-1))   (p == 1)
+__device__ __forceinline__ float axis_scale(float a1, float a2, int dim, int p) {
+    return (p > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), (float)(dim - 1)), (float)(p - 1)) : 0.0f;
+}
+__device__ __forceinline__ float axis_coord(float a1, float a2, int dim, int p, int k, float scale) {
+    if (p > 1) return __fadd_rn(__fmul_rn(a1, (float)(dim - 1)), __fmul_rn((float)k, scale));
+    return (float)__dmul_rn(__dmul_rn((double)__fadd_rn(a1, a2), 0.5), (double)(dim - 1));
+}
+__device__ __forceinline__ bool axis_invalid(float in, int dim) {
+    return in < 0.0f || in > (float)(dim - 1);
+}
+
+// a + (b - a) * t with three roundings, as the reference's subss/mulss/addss
+__device__ __forceinline__ float lerp_rn(float a, float b, float t) {
+    return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+}
+__device__ __forceinline__ float4 lerp_rn(const float4 a, const float4 b, float t) {
+    return make_float4(lerp_rn(a.x, b.x, t), lerp_rn(a.y, b.y, t), lerp_rn(a.z, b.z, t), lerp_rn(a.w, b.w, t));
+}
+
+// ---- memory helpers ---------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+// streaming (evict-first) 128-bit store: crops / grads are written once and not re-read here
+__device__ __forceinline__ void st_stream4(float *p, const float4 v) {
+    __stcs(reinterpret_cast<float4 *>(p), v);
+}
+// vectorised fire-and-forget global reduction (sm_90+): one 16-byte RED per 4 channels
+__device__ __forceinline__ void red_add4(float *p, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add1(float *p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// ---- geometry + kernel launchers (defined in roi3d_car_*.cu / roi3d_nms.cu) ------
+struct CarGeom {
+    int B, H, W, D, C;      // volume [B,H,W,D,C]
+    int n, ph, pw, pd;      // n boxes, crop size
+};
+
+int launch_car3d_fwd_direct(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                            int method, float ext, float *crops, cudaStream_t stream);
+int launch_car3d_grad_image_direct(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
+                                   int method, float *grad_image, cudaStream_t stream);
+int launch_car3d_grad_boxes(const float *grads, const float *image, const float *boxes, const int *box_ind,
+                            const CarGeom &g, float *grad_boxes, cudaStream_t stream);
+int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                           float ext, float *crops, cudaStream_t stream);
+int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
+                                  float *grad_image, cudaStream_t stream);
+size_t nms3d_workspace_bytes(int n);
+int launch_nms3d(const float *boxes, const float *scores, int n, int max_out, float thr,
+                 int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace roi3d

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's ``core/custom_op`` surface on B200.
+
+The reference imports four callables (core/custom_op/custom_op.py:22-25) and
+registers one gradient (core/custom_op/custom_op.py:28-65):
+
+    crop_and_resize_3d(image, boxes, box_index, crop_size)                 core/models.py:663-664, 992-994
+    crop_and_resize_3d_grad_image(grads, boxes, box_ind, image_size, T=, method_name=)
+    crop_and_resize_3d_grad_boxes(grads, image, boxes, box_ind)
+    non_max_suppression_3d(boxes, scores, max_output_size, iou_threshold)   core/models.py:453-455
+
+This module exposes the same names with the same argument meaning, layouts
+(boxes ``[N,6] = (y1,x1,z1,y2,x2,z2)`` normalized; volumes ``[B,H,W,D,C]``
+channel-last float32) and the same validation messages as the reference ops'
+``OP_REQUIRES`` checks (raised as :class:`InvalidArgumentError`).  TensorFlow is
+not available in this image, so tensors are ``torch`` CUDA tensors (device
+memory + streams only; every computation happens in the hand-written sm_100a
+kernels behind the C ABI of ``include/roi3d.h``).  Host buffers (numpy arrays or
+CPU tensors) are also accepted: they are copied host->device through pinned
+memory, computed on the GPU and copied back -- the end-to-end path a CPU-op
+drop-in sees.  There is no CPU fallback: without a CUDA device or without the
+built library every call raises.
+
+The TF-side registration that makes ``core/models.py`` load this library
+unchanged is in ``tf_ops/``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = [
+    "InvalidArgumentError", "crop_and_resize_3d", "crop_and_resize_3d_grad_image",
+    "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
+    "set_option", "get_option", "kernel_launches", "reset_kernel_launches",
+]
+
+METHODS = {"trilinear": 0, "nearest": 1}
+
+
+class InvalidArgumentError(ValueError):
+    """Mirror of tf.errors.InvalidArgumentError raised by the reference ops' OP_REQUIRES."""
+
+
+def _require(cond, msg):
+    if not cond:
+        raise InvalidArgumentError(msg)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("roi3d_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t.numel() else 0)
+
+
+def _shape(x):
+    """Shape of a torch tensor / numpy array / nested list without touching the device."""
+    return tuple(x.shape) if hasattr(x, "shape") else tuple(np.asarray(x).shape)
+
+
+class _Arg:
+    """Brings one argument to the device; remembers whether the caller passed a host buffer."""
+
+    __slots__ = ("dev", "host", "numpy")
+
+    def __init__(self, x, dtype, device):
+        self.numpy = isinstance(x, np.ndarray) or not isinstance(x, torch.Tensor)
+        t = torch.as_tensor(x) if self.numpy else x
+        self.host = t.device.type != "cuda"
+        if self.host:
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            t = t.contiguous()
+            if not t.is_pinned() and t.numel() * t.element_size() >= (1 << 16):
+                t = t.pin_memory()                     # pageable -> pinned staging, then one async H2D
+            self.dev = t.to(device, non_blocking=True)
+        else:
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            self.dev = t.contiguous()
+
+
+def _finish(out, host, as_numpy):
+    """Return `out` where the caller's inputs lived (device stays device, host gets a pinned copy)."""
+    if not host:
+        return out
+    res = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    res.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return res.numpy() if as_numpy else res
+
+
+# ---------------------------------------------------------------------------------------
+# NonMaxSuppression3D
+# ---------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def non_max_suppression_3d(boxes, scores, max_output_size, iou_threshold=0.5, name=None):
+    """Greedy 3-D NMS; returns int32 ``[M]`` selected indices in selection order, M <= max_output_size.
+
+    Mirrors REGISTER_OP("NonMaxSuppression3D") (NMS.so@0xe4e0): ``iou_threshold`` is an attr
+    (python float), ``max_output_size`` a 0-D int.  Bit-exact with the reference (same IoU
+    arithmetic, suppression on ``iou >= threshold``, ties -> lower index first).
+    """
+    del name
+    bs, ss = _shape(boxes), _shape(scores)
+    _require(len(bs) == 2, "boxes must be 2-D")
+    _require(bs[1] == 6, "boxes must have 6 columns")
+    _require(len(ss) == 1, "scores must be 1-D")
+    _require(ss[0] == bs[0], "scores has incompatible shape")
+    mos = np.asarray(max_output_size.cpu() if isinstance(max_output_size, torch.Tensor) else max_output_size)
+    _require(mos.ndim == 0, "max_output_size must be 0-D, got shape %s" % (list(mos.shape),))
+    thr = float(iou_threshold)
+    _require(0.0 <= thr <= 1.0, "iou_threshold must be in [0, 1]")
+    dev = _device()
+    b, s = _Arg(boxes, torch.float32, dev), _Arg(scores, torch.float32, dev)
+    n, max_out = int(b.dev.shape[0]), max(int(mos), 0)
+    host = b.host or s.host
+    lib = _lib.load()
+    keep = torch.empty(max(max_out, 1), dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+    if n > 0 and max_out > 0:
+        nbytes = lib.roi3d_nms3d_workspace_bytes(n)
+        ws = _workspace(nbytes, dev)
+        _lib.check(lib.roi3d_nms3d(_ptr(b.dev), _ptr(s.dev), n, max_out, thr, _ptr(keep), _ptr(count),
+                                   _ptr(ws), ws.numel(), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()      # output length is data dependent
+    m = int(count[0])
+    return _finish(keep[:m], host, b.numpy)
+
+
+# ---------------------------------------------------------------------------------------
+# CropAndResize3D family
+# ---------------------------------------------------------------------------------------
+def _check_boxes(boxes, box_index):
+    b, bi = _shape(boxes), _shape(box_index)
+    _require(len(b) == 2, "boxes must be 2-D")
+    _require(b[1] == 6, "boxes must have 6 columns")
+    _require(len(bi) == 1, "box_index must be 1-D")
+    _require(bi[0] == b[0], "box_index has incompatible shape")
+
+
+def _method(method_name):
+    _require(method_name in METHODS, "method must be 'trilinear' or 'nearest'")
+    return METHODS[method_name]
+
+
+def _crop_size(crop_size):
+    cs = np.asarray(crop_size.cpu() if isinstance(crop_size, torch.Tensor) else crop_size)
+    _require(cs.ndim == 1, "crop_size must be 1-D")
+    _require(cs.shape[0] == 3, "crop_size must have three elements")
+    ph, pw, pd = (int(v) for v in cs)
+    _require(ph > 0 and pw > 0 and pd > 0, "crop dimensions must be positive")
+    return ph, pw, pd
+
+
+def _fwd_device(image, boxes, box_index, crop, method, ext):
+    B, H, W, D, C = image.shape
+    n = boxes.shape[0]
+    out = torch.empty((n,) + crop + (C,), dtype=torch.float32, device=image.device)
+    lib = _lib.load()
+    _lib.check(lib.roi3d_car3d_fwd(_ptr(image), B, H, W, D, C, _ptr(boxes), _ptr(box_index), n,
+                                   crop[0], crop[1], crop[2], method, float(ext), _ptr(out), _stream_ptr()))
+    return out
+
+
+def _grad_image_device(grads, boxes, box_ind, image_size, method):
+    B, H, W, D, C = image_size
+    n, ph, pw, pd = grads.shape[:4]
+    out = torch.empty((B, H, W, D, C), dtype=torch.float32, device=grads.device)
+    lib = _lib.load()
+    _lib.check(lib.roi3d_car3d_grad_image(_ptr(grads), _ptr(boxes), _ptr(box_ind), n, ph, pw, pd,
+                                          B, H, W, D, C, method, _ptr(out), _stream_ptr()))
+    return out
+
+
+def _grad_boxes_device(grads, image, boxes, box_ind):
+    B, H, W, D, C = image.shape
+    n, ph, pw, pd = grads.shape[:4]
+    out = torch.zeros((n, 6), dtype=torch.float32, device=grads.device)
+    lib = _lib.load()
+    _lib.check(lib.roi3d_car3d_grad_boxes(_ptr(grads), _ptr(image), B, H, W, D, C, _ptr(boxes), _ptr(box_ind), n,
+                                          ph, pw, pd, _ptr(out), _stream_ptr()))
+    return out
+
+
+class CropAndResize3DFunction(torch.autograd.Function):
+    """Autograd wiring equal to ``_CropAndResize3DGrad`` (core/custom_op/custom_op.py:28-65):
+    d/d image through CropAndResize3DGradImage, d/d boxes through CropAndResize3DGradBoxes
+    (always the trilinear approximation), None for box_index and crop_size."""
+
+    @staticmethod
+    def forward(ctx, image, boxes, box_index, crop, method, ext):
+        ctx.save_for_backward(image, boxes, box_index)
+        ctx.method = method
+        return _fwd_device(image, boxes, box_index, crop, method, ext)
+
+    @staticmethod
+    def backward(ctx, grad):
+        image, boxes, box_index = ctx.saved_tensors
+        grad = grad.contiguous()
+        grad0 = grad1 = None
+        if ctx.needs_input_grad[0]:
+            grad0 = _grad_image_device(grad, boxes, box_index, tuple(image.shape), ctx.method)
+        if ctx.needs_input_grad[1]:
+            grad1 = _grad_boxes_device(grad, image, boxes, box_index)
+        return grad0, grad1, None, None, None, None
+
+
+def crop_and_resize_3d(image, boxes, box_index, crop_size, method_name="trilinear",
+                       extrapolation_value=0.0, name=None):
+    """Trilinear (or nearest) crop of ``image [B,H,W,D,C]`` by ``boxes [N,6]`` -> ``[N,ph,pw,pd,C]``.
+
+    Mirrors REGISTER_OP("CropAndResize3D") (CAR.so@0x4370).  Differentiable w.r.t. ``image``
+    and ``boxes`` when they are CUDA tensors requiring grad.
+    """
+    del name
+    method = _method(method_name)
+    ims = _shape(image)
+    _require(len(ims) == 5, "input image must be 5-D")
+    _check_boxes(boxes, box_index)
+    crop = _crop_size(crop_size)
+    _require(all(int(d) > 0 for d in ims[1:4]), "image dimensions must be positive")
+    dev = _device()
+    im, b, bi = _Arg(image, torch.float32, dev), _Arg(boxes, torch.float32, dev), _Arg(box_index, torch.int32, dev)
+    host = im.host or b.host or bi.host
+    if not host and (im.dev.requires_grad or b.dev.requires_grad):
+        return CropAndResize3DFunction.apply(im.dev, b.dev, bi.dev, crop, method, float(extrapolation_value))
+    out = _fwd_device(im.dev, b.dev, bi.dev, crop, method, extrapolation_value)
+    return _finish(out, host, im.numpy)
+
+
+def crop_and_resize_3d_grad_image(grads, boxes, box_ind, image_size, T=None, method_name="trilinear", name=None):
+    """Gradient of :func:`crop_and_resize_3d` w.r.t. the image: ``[B,H,W,D,C]`` float32.
+
+    Mirrors REGISTER_OP("CropAndResize3DGradImage") (GI.so@0x3a80).  ``T`` is accepted for
+    signature compatibility; like the reference kernel only float32 is computed.
+    """
+    del name
+    if T is not None and T not in (torch.float32, np.float32, "float32", "float"):
+        raise InvalidArgumentError("CropAndResize3DGradImage: only T=float32 is implemented")
+    method = _method(method_name)
+    gs = _shape(grads)
+    _require(len(gs) == 5, "grads image must be 5-D")
+    _check_boxes(boxes, box_ind)
+    isz = np.asarray(image_size.cpu() if isinstance(image_size, torch.Tensor) else image_size)
+    _require(isz.ndim == 1, "image_size must be 1-D")
+    _require(isz.shape[0] == 5, "image_size must have five elements")
+    size = tuple(int(v) for v in isz)
+    if gs[0] > 0:
+        _require(all(int(d) > 0 for d in gs[1:4]), "grads dimensions must be positive")
+    _require(all(d > 0 for d in size[1:4]), "image dimensions must be positive")
+    _require(size[4] == gs[4], "image_size and grads are incompatible")
+    _require(_shape(boxes)[0] == gs[0], "boxes and grads have incompatible shape")
+    dev = _device()
+    g, b, bi = _Arg(grads, torch.float32, dev), _Arg(boxes, torch.float32, dev), _Arg(box_ind, torch.int32, dev)
+    host = g.host or b.host or bi.host
+    out = _grad_image_device(g.dev, b.dev, bi.dev, size, method)
+    return _finish(out, host, g.numpy)
+
+
+def crop_and_resize_3d_grad_boxes(grads, image, boxes, box_ind, method_name="trilinear", name=None):
+    """Gradient of :func:`crop_and_resize_3d` w.r.t. the boxes: ``[N,6]`` float32 (trilinear only).
+
+    Mirrors REGISTER_OP("CropAndResize3DGradBoxes") (GB.so@0x3980).
+    """
+    del name
+    _require(method_name == "trilinear", "method must be 'trilinear' or 'nearest'")
+    gs, ims = _shape(grads), _shape(image)
+    _require(len(gs) == 5, "grads image must be 5-D")
+    _require(len(ims) == 5, "input image must be 5-D")
+    _check_boxes(boxes, box_ind)
+    if gs[0] > 0:
+        _require(all(int(d) > 0 for d in gs[1:4]), "grads dimensions must be positive")
+    _require(all(int(d) > 0 for d in ims[1:4]), "image dimensions must be positive")
+    _require(ims[4] == gs[4], "image and grads depths are incompatible")
+    _require(_shape(boxes)[0] == gs[0], "boxes and grads have incompatible shape")
+    dev = _device()
+    g, im = _Arg(grads, torch.float32, dev), _Arg(image, torch.float32, dev)
+    b, bi = _Arg(boxes, torch.float32, dev), _Arg(box_ind, torch.int32, dev)
+    host = g.host or im.host or b.host or bi.host
+    out = _grad_boxes_device(g.dev, im.dev, b.dev, bi.dev)
+    return _finish(out, host, g.numpy)
+
+
+# ---------------------------------------------------------------------------------------
+# tuning / introspection passthroughs
+# ---------------------------------------------------------------------------------------
+def set_option(name, value):
+    _lib.check(_lib.load().roi3d_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = ctypes.c_int(0)
+    _lib.check(_lib.load().roi3d_get_option(name.encode(), ctypes.byref(v)))
+    return v.value
+
+
+def kernel_launches():
+    return int(_lib.load().roi3d_kernel_launches())
+
+
+def reset_kernel_launches():
+    _lib.load().roi3d_reset_kernel_launches()

@@ -1,0 +1,144 @@
+/*
+ * roi3d.h -- C ABI of the B200-native ROI hot path of 3D Mask R-CNN
+ * (libroi3d_b200.so, hand-written sm_100a CUDA; no CPU fallback).
+ *
+ * This is the drop-in boundary.  Each entry point is what the reference's
+ * TensorFlow custom-op kernels for this path would bind instead of their own
+ * CPU loops.  The reference ships those kernels only as a prebuilt wheel
+ * (core/custom_op/tensorflow_nms_car_3d-0.1.0-cp36-cp36m-linux_x86_64.whl);
+ * "replaces" cites the op registration / OpKernel::Compute inside the wheel's
+ * shared objects (notation <lib>@0xADDR) and the Python
+ * call site in the reference tree.
+ *
+ * Conventions (identical to the reference ops):
+ *   boxes   float32 [N,6] = (y1,x1,z1,y2,x2,z2), normalized to [0,1];
+ *           normalized -> voxel is coord * (dim - 1).
+ *   image   float32 [B,H,W,D,C], channel-last; y<->H, x<->W, z<->D.
+ *   crops   float32 [N,ph,pw,pd,C].
+ *   method  0 = "trilinear", 1 = "nearest".
+ *
+ * Ownership / threading: every pointer is a DEVICE pointer on the current CUDA
+ * device unless stated otherwise and is owned by the caller (TF allocator,
+ * torch, cudaMalloc ...).  The library allocates nothing, keeps no pointer and
+ * has no mutable global state: all calls are re-entrant.  All work is enqueued
+ * on `stream` (a cudaStream_t passed as void*); no call synchronizes the device
+ * or the stream.  Return value: ROI3D_OK or a negative ROI3D_E* code; nothing
+ * is thrown and nothing aborts.
+ */
+#ifndef ROI3D_H_
+#define ROI3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ROI3D_API
+#else
+#define ROI3D_API __attribute__((visibility("default")))
+#endif
+
+typedef void *roi3d_stream_t;            /* cudaStream_t */
+
+enum {
+    ROI3D_OK            = 0,
+    ROI3D_EINVAL        = -1,            /* bad argument (NULL, negative size, bad method ...) */
+    ROI3D_EWORKSPACE    = -2,            /* workspace missing, too small or misaligned */
+    ROI3D_EUNSUPPORTED  = -3,            /* shape beyond what the kernels index */
+    ROI3D_ECUDA         = -4             /* a CUDA launch/runtime error; see roi3d_last_cuda_error() */
+};
+
+enum { ROI3D_METHOD_TRILINEAR = 0, ROI3D_METHOD_NEAREST = 1 };
+
+ROI3D_API const char *roi3d_version(void);
+ROI3D_API const char *roi3d_strerror(int code);
+/* cudaError_t of the most recent ROI3D_ECUDA on the calling thread (0 if none). */
+ROI3D_API int roi3d_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------
+ * NonMaxSuppression3D
+ * replaces: REGISTER_OP("NonMaxSuppression3D") + NonMaxSuppression3DOp<CPUDevice>::Compute
+ *           (NMS.so@0xe4e0) -> DoNonMaxSuppressionOp<float> (NMS.so@0xd0c0) with
+ *           IOU<float> (NMS.so@0xb500); Python: core/custom_op/custom_op.py:25,
+ *           called from core/models.py:453-455 and core/utils.py:498-500.
+ *
+ * Greedy hard NMS over `n` boxes: candidates are visited by descending score
+ * (ties: lower index first; scores <= -FLT_MAX or NaN are never candidates); a
+ * candidate is dropped when its 3-D IoU with an already selected box is
+ * >= iou_thr; stops after max_out selections.  keep_idx receives the selected
+ * ORIGINAL indices in selection order (capacity >= min(n,max_out) ints... see
+ * note), *keep_count their number.  The reference's zero-volume quirk (a
+ * selected box with volume <= 0 is emitted repeatedly until max_out, SURVEY.md
+ * section 8 row a2) is reproduced, so keep_idx needs capacity max_out when that can
+ * happen; capacity max(1, max_out) is always safe.
+ *
+ * keep_count may be a device pointer or a pinned/mapped host pointer (it is
+ * written by a kernel).  The caller must synchronize `stream` before reading
+ * it -- the one sync this path needs, because the output length is data
+ * dependent.
+ * workspace: roi3d_nms3d_workspace_bytes(n) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------- */
+ROI3D_API size_t roi3d_nms3d_workspace_bytes(int n);
+ROI3D_API int roi3d_nms3d(const float *boxes, const float *scores, int n, int max_out, float iou_thr,
+                          int *keep_idx, int *keep_count,
+                          void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * CropAndResize3D (forward)
+ * replaces: REGISTER_OP("CropAndResize3D") + CropAndResize3DOp::Compute (CAR.so@0x4370);
+ *           Python: core/custom_op/custom_op.py:22, called from core/models.py:663-664
+ *           (PyramidROIAlign) and core/models.py:992-994 (mask targets).
+ * box_index[i] selects the batch item of box i and must lie in [0,B) (the
+ * reference does not check it either).  n == 0 is valid (nothing is launched).
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
+                              const float *boxes, const int *box_index, int n,
+                              int ph, int pw, int pd, int method, float extrapolation_value,
+                              float *crops, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * CropAndResize3DGradImage
+ * replaces: REGISTER_OP("CropAndResize3DGradImage") + CropAndResize3DGradImageOp::Compute
+ *           (GI.so@0x3a80); Python: core/custom_op/custom_op.py:24,52-53.
+ * grad_image [B,H,W,D,C] is zero-filled by the call, then every in-range crop
+ * voxel scatter-adds its gradient to its 8 (trilinear) or 1 (nearest) taps.
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *box_ind, int n,
+                                     int ph, int pw, int pd,
+                                     int B, int H, int W, int D, int C, int method,
+                                     float *grad_image, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * CropAndResize3DGradBoxes (trilinear only, like the reference)
+ * replaces: REGISTER_OP("CropAndResize3DGradBoxes") + CropAndResize3DGradBoxesOp::Compute
+ *           (GB.so@0x3980); Python: core/custom_op/custom_op.py:23,63.
+ * grad_boxes [N,6] is fully written by the call.
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_car3d_grad_boxes(const float *grads, const float *image,
+                                     int B, int H, int W, int D, int C,
+                                     const float *boxes, const int *box_ind, int n,
+                                     int ph, int pw, int pd,
+                                     float *grad_boxes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Tuning / introspection (not part of the reference surface).
+ * roi3d_set_option: process-wide knobs used by the benchmarks and tests to
+ * select a kernel variant; the defaults are the production choice.
+ *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable
+ *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
+ * Returns ROI3D_EINVAL for an unknown name.  roi3d_kernel_launches() returns
+ * the number of kernel launches this library has enqueued on the calling
+ * thread since the last roi3d_reset_kernel_launches().
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_set_option(const char *name, int value);
+ROI3D_API int roi3d_get_option(const char *name, int *value);
+ROI3D_API long long roi3d_kernel_launches(void);
+ROI3D_API void roi3d_reset_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROI3D_H_ */

@@ -1,0 +1,154 @@
+"""CPU oracle for the ROI hot path -- TEST INFRASTRUCTURE, not product code.
+
+ctypes front-end of ``oracle/roi3d_oracle.c`` (a restatement of the reference's
+four native ops, see the header of that file for the binary addresses each
+function follows).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+package; the product package ``3d-mask-r-cnn_b200/`` never does.
+
+All functions take and return numpy arrays in the reference's layouts:
+boxes ``float32 [N,6] = (y1,x1,z1,y2,x2,z2)`` normalized, volumes
+``float32 [B,H,W,D,C]`` channel-last, crops ``float32 [N,ph,pw,pd,C]``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int)
+
+METHODS = {"trilinear": 0, "nearest": 1}
+
+
+def build(force=False):
+    """Compile oracle/roi3d_oracle.c (plain + OpenMP flavours) with gcc."""
+    plain = os.path.join(_BUILD, "libroi3d_oracle.so")
+    omp = os.path.join(_BUILD, "libroi3d_oracle_omp.so")
+    src = os.path.join(_HERE, "roi3d_oracle.c")
+    stale = force or not (os.path.exists(plain) and os.path.exists(omp)) or \
+        os.path.getmtime(src) > min(os.path.getmtime(plain), os.path.getmtime(omp))
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return plain, omp
+
+
+_libs = {}
+
+
+def _lib(omp=False):
+    key = bool(omp)
+    if key not in _libs:
+        plain, ompp = build()
+        lib = ctypes.CDLL(ompp if omp else plain)
+        lib.roi3d_oracle_iou3d.restype = ctypes.c_float
+        lib.roi3d_oracle_iou3d.argtypes = [_f32p, ctypes.c_int, ctypes.c_int]
+        lib.roi3d_oracle_nms3d.restype = ctypes.c_int
+        lib.roi3d_oracle_nms3d.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_float, _i32p]
+        lib.roi3d_oracle_car3d_fwd.restype = None
+        lib.roi3d_oracle_car3d_fwd.argtypes = [_f32p] + [ctypes.c_int] * 5 + [_f32p, _i32p] + \
+            [ctypes.c_int] * 5 + [ctypes.c_float, _f32p, ctypes.c_int]
+        lib.roi3d_oracle_car3d_grad_image.restype = None
+        lib.roi3d_oracle_car3d_grad_image.argtypes = [_f32p, _f32p, _i32p] + [ctypes.c_int] * 10 + \
+            [_f32p, ctypes.c_int]
+        lib.roi3d_oracle_car3d_grad_boxes.restype = None
+        lib.roi3d_oracle_car3d_grad_boxes.argtypes = [_f32p, _f32p] + [ctypes.c_int] * 5 + [_f32p, _i32p] + \
+            [ctypes.c_int] * 4 + [_f32p]
+        lib.roi3d_oracle_iou_matrix.restype = None
+        lib.roi3d_oracle_iou_matrix.argtypes = [_f32p, ctypes.c_int, _f32p]
+        lib.roi3d_oracle_max_threads.restype = ctypes.c_int
+        _libs[key] = lib
+    return _libs[key]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i32p)
+
+
+def max_threads():
+    return int(_lib(True).roi3d_oracle_max_threads())
+
+
+def iou3d(boxes, i, j):
+    boxes = _f32(boxes)
+    return float(_lib().roi3d_oracle_iou3d(_fp(boxes), int(i), int(j)))
+
+
+def iou_matrix(boxes):
+    boxes = _f32(boxes).reshape(-1, 6)
+    n = boxes.shape[0]
+    out = np.empty((n, n), np.float32)
+    _lib().roi3d_oracle_iou_matrix(_fp(boxes), n, _fp(out))
+    return out
+
+
+def non_max_suppression_3d(boxes, scores, max_output_size, iou_threshold=0.5):
+    """Reference NonMaxSuppression3D (NMS.so@0xe4e0 -> 0xd0c0): int32 [M]."""
+    boxes = _f32(boxes).reshape(-1, 6)
+    scores = _f32(scores).reshape(-1)
+    n = boxes.shape[0]
+    assert scores.shape[0] == n
+    out = np.empty(max(int(max_output_size), 1), np.int32)
+    m = _lib().roi3d_oracle_nms3d(_fp(boxes), _fp(scores), n, int(max_output_size),
+                                  float(iou_threshold), _ip(out))
+    return out[:m].copy()
+
+
+def crop_and_resize_3d(image, boxes, box_index, crop_size, method_name="trilinear",
+                       extrapolation_value=0.0, threads=1):
+    """Reference CropAndResize3D (CAR.so@0x4370): float32 [N,ph,pw,pd,C]."""
+    image = _f32(image)
+    boxes = _f32(boxes).reshape(-1, 6)
+    box_index = _i32(box_index).reshape(-1)
+    B, H, W, D, C = image.shape
+    ph, pw, pd = (int(v) for v in crop_size)
+    n = boxes.shape[0]
+    out = np.empty((n, ph, pw, pd, C), np.float32)
+    _lib(threads > 1).roi3d_oracle_car3d_fwd(_fp(image), B, H, W, D, C, _fp(boxes), _ip(box_index), n,
+                                            ph, pw, pd, METHODS[method_name], float(extrapolation_value),
+                                            _fp(out), int(threads))
+    return out
+
+
+def crop_and_resize_3d_grad_image(grads, boxes, box_ind, image_size, method_name="trilinear", threads=1):
+    """Reference CropAndResize3DGradImage (GI.so@0x3a80): float32 [B,H,W,D,C]."""
+    grads = _f32(grads)
+    boxes = _f32(boxes).reshape(-1, 6)
+    box_ind = _i32(box_ind).reshape(-1)
+    B, H, W, D, C = (int(v) for v in image_size)
+    n, ph, pw, pd, Cg = grads.shape
+    assert Cg == C and boxes.shape[0] == n
+    out = np.empty((B, H, W, D, C), np.float32)
+    _lib(threads > 1).roi3d_oracle_car3d_grad_image(_fp(grads), _fp(boxes), _ip(box_ind), n, ph, pw, pd,
+                                                   B, H, W, D, C, METHODS[method_name], _fp(out), int(threads))
+    return out
+
+
+def crop_and_resize_3d_grad_boxes(grads, image, boxes, box_ind):
+    """Reference CropAndResize3DGradBoxes (GB.so@0x3980): float32 [N,6]."""
+    grads = _f32(grads)
+    image = _f32(image)
+    boxes = _f32(boxes).reshape(-1, 6)
+    box_ind = _i32(box_ind).reshape(-1)
+    B, H, W, D, C = image.shape
+    n, ph, pw, pd, _ = grads.shape
+    out = np.empty((n, 6), np.float32)
+    _lib().roi3d_oracle_car3d_grad_boxes(_fp(grads), _fp(image), B, H, W, D, C, _fp(boxes), _ip(box_ind), n,
+                                         ph, pw, pd, _fp(out))
+    return out

@@ -1,0 +1,317 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI via the host-side mirror of
+core/custom_op) against the CPU oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star):
+  NMS3D kept indices + order ............ bit-exact
+  CropAndResize3D forward ............... <= 1e-5 relative  (and, in fact, bit-exact: asserted)
+  CropAndResize3DGradImage .............. <= 1e-4 relative  (atomic re-ordering)
+"relative" = |a-b| <= tol * max(|b|, 1e-3 * max|b|) elementwise.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import roi3d_synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FWD_TOL, BWD_TOL, GB_TOL = 1e-5, 1e-4, 2e-3
+
+
+def rel_ok(a, b, tol):
+    b = np.asarray(b, np.float64)
+    a = np.asarray(a, np.float64)
+    scale = np.maximum(np.abs(b), 1e-3 * (np.abs(b).max() if b.size else 0.0))
+    return bool(np.all(np.abs(a - b) <= tol * scale + 1e-30))
+
+
+def dev(x, cuda_device):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(cuda_device)
+
+
+@pytest.fixture(autouse=True)
+def _reset_variants(rb):
+    yield
+    rb.custom_op.set_option("car_fwd_variant", 0)
+    rb.custom_op.set_option("car_bwd_variant", 0)
+
+
+# =============================================================================================
+# NMS3D
+# =============================================================================================
+def run_nms(rb, cuda_device, boxes, scores, max_out, thr):
+    keep = rb.non_max_suppression_3d(dev(boxes, cuda_device), dev(scores, cuda_device), max_out, thr)
+    assert keep.dtype.is_floating_point is False and keep.dim() == 1
+    return keep.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,thr,max_out,presorted", [
+    (1, 0.5, 10, False), (2, 0.5, 1, False), (31, 0.5, 31, False), (32, 0.3, 100, False), (33, 0.7, 5, True),
+    (257, 0.5, 64, False), (1000, 0.3, 1000, False), (1000, 0.7, 100, True), (4097, 0.5, 300, False),
+    (6000, 0.7, 1000, True), (6000, 0.7, 1000, False), (6000, 0.3, 6000, False), (20000, 0.7, 2000, False),
+])
+def test_nms_matches_oracle(rb, cuda_device, n, thr, max_out, presorted):
+    boxes, scores = roi3d_synth.nms_boxes(n, (128, 128, 128), seed=900 + n, presorted=presorted)
+    got = run_nms(rb, cuda_device, boxes, scores, max_out, thr)
+    ref = oracle.non_max_suppression_3d(boxes, scores, max_out, thr)
+    assert np.array_equal(got, ref)
+
+
+def test_nms_golden(rb, cuda_device):
+    z = np.load(os.path.join(GOLDEN, "nms.npz"))
+    for n in (300, 1000, 64):
+        mo, thr = z["args_%d" % n]
+        got = run_nms(rb, cuda_device, z["boxes_%d" % n], z["scores_%d" % n], int(mo), float(thr))
+        assert np.array_equal(got, z["keep_%d" % n])
+
+
+def test_nms_edge_cases(rb, cuda_device):
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 0.9], [0, 0, 0, 1, 1, 0.5], [2, 2, 2, 3, 3, 3]], np.float32)
+    scores = np.array([0.9, 0.8, 0.7, 0.1], np.float32)
+    for thr, mo in ((0.6, 10), (0.5, 10), (0.6, 2), (0.0, 10), (1.0, 10), (0.6, 0)):
+        assert run_nms(rb, cuda_device, boxes, scores, mo, thr).tolist() == \
+            oracle.non_max_suppression_3d(boxes, scores, mo, thr).tolist()
+    # empty input
+    assert run_nms(rb, cuda_device, np.zeros((0, 6), np.float32), np.zeros(0, np.float32), 5, 0.5).tolist() == []
+    # ties (incl. -0.0 == +0.0) -> lower index first
+    b3 = np.array([[0, 0, 0, 1, 1, 1], [5, 5, 5, 6, 6, 6], [0, 0, 0, 1, 1, 1]], np.float32)
+    assert run_nms(rb, cuda_device, b3, np.array([0.5, 0.5, 0.5], np.float32), 3, 0.5).tolist() == [0, 1]
+    assert run_nms(rb, cuda_device, b3, np.array([0.0, -0.0, 0.0], np.float32), 3, 0.5).tolist() == [0, 1]
+    # scores <= -FLT_MAX / NaN are never candidates
+    s = np.array([-np.inf, np.nan, 0.1], np.float32)
+    assert run_nms(rb, cuda_device, b3, s, 5, 0.5).tolist() == oracle.non_max_suppression_3d(b3, s, 5, 0.5).tolist() == [2]
+    # negative scores, reversed corners
+    bx, sc = roi3d_synth.nms_boxes(500, (64, 64, 64), seed=77)
+    bx[::3] = bx[::3][:, [3, 4, 5, 0, 1, 2]]
+    sc = sc - 0.5
+    assert np.array_equal(run_nms(rb, cuda_device, bx, sc, 200, 0.4), oracle.non_max_suppression_3d(bx, sc, 200, 0.4))
+
+
+def test_nms_zero_volume_quirk(rb, cuda_device):
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [0.2, 0.2, 0.2, 0.2, 0.5, 0.5], [3, 3, 3, 4, 4, 4]], np.float32)
+    scores = np.array([0.9, 0.8, 0.7], np.float32)
+    for thr, mo in ((0.5, 5), (0.0, 5), (0.5, 2), (0.5, 1)):
+        assert run_nms(rb, cuda_device, boxes, scores, mo, thr).tolist() == \
+            oracle.non_max_suppression_3d(boxes, scores, mo, thr).tolist()
+    bx, sc = roi3d_synth.nms_boxes(300, (64, 64, 64), seed=78)
+    bx[40, 3] = bx[40, 0]                                     # a zero-volume box somewhere in the middle
+    assert np.array_equal(run_nms(rb, cuda_device, bx, sc, 250, 0.5), oracle.non_max_suppression_3d(bx, sc, 250, 0.5))
+
+
+def test_nms_many_duplicates(rb, cuda_device):
+    bx, _ = roi3d_synth.nms_boxes(3000, (128, 128, 128), seed=79)
+    sc = np.random.default_rng(79).integers(0, 7, 3000).astype(np.float32) / 7.0     # heavy ties
+    assert np.array_equal(run_nms(rb, cuda_device, bx, sc, 3000, 0.5), oracle.non_max_suppression_3d(bx, sc, 3000, 0.5))
+
+
+def test_nms_large_properties(rb, cuda_device):
+    """100k boxes (BASELINE sweep max): properties that do not need the oracle."""
+    n, thr = 100000, 0.5
+    boxes, scores = roi3d_synth.nms_boxes(n, (256, 256, 256), seed=80)
+    keep = run_nms(rb, cuda_device, boxes, scores, 2000, thr)
+    assert len(keep) == 2000 and len(set(keep.tolist())) == 2000
+    ks = scores[keep]
+    assert np.all(ks[:-1] >= ks[1:])                            # selection order = score order
+    iou = oracle.iou_matrix(boxes[keep])
+    np.fill_diagonal(iou, 0.0)
+    assert iou.max() < thr                                      # kept set is conflict free
+    again = run_nms(rb, cuda_device, boxes[keep], scores[keep], 2000, thr)
+    assert np.array_equal(again, np.arange(2000))               # idempotent
+    # every dropped box ranked above the last kept one is suppressed by a kept box with higher priority
+    order = np.lexsort((np.arange(n), -scores.astype(np.float64)))
+    rank = np.empty(n, np.int64)
+    rank[order] = np.arange(n)
+    cut = rank[keep[-1]]
+    dropped = order[:cut][~np.isin(order[:cut], keep)]
+    sample = dropped[:: max(1, len(dropped) // 200)]
+    both = np.concatenate([boxes[keep], boxes[sample]])
+    m = oracle.iou_matrix(both)[2000:, :2000]
+    for r, d in enumerate(sample):
+        assert np.any((m[r] >= thr) & (rank[keep] < rank[d]))
+
+
+# =============================================================================================
+# CropAndResize3D
+# =============================================================================================
+def car_inputs(seed, B, H, W, D, C, n, crop, wild=True):
+    rng = np.random.default_rng(seed)
+    image = rng.standard_normal((B, H, W, D, C), dtype=np.float32)
+    boxes = roi3d_synth.rois(n, (H * 4, W * 4, D), seed, side_px=(4.0, 3.0 * max(H, W)))
+    if wild and n >= 6:
+        boxes[0] = [-0.2, 0.1, 0.1, 0.7, 1.3, 0.9]            # partly outside -> extrapolation
+        boxes[1] = [0.8, 0.7, 0.9, 0.2, 0.1, 0.3]             # reversed corners
+        boxes[2] = [0.5, 0.5, 0.5, 0.5, 0.5, 0.5]             # zero size
+        boxes[3] = [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]             # whole volume, integer coordinates
+        boxes[4] = [1.2, 1.2, 1.2, 1.5, 1.5, 1.5]             # fully outside
+        boxes[5] = [0.25, 0.25, 0.25, 0.75, 0.75, 0.75]
+    box_index = rng.integers(0, B, n).astype(np.int32)
+    grads = rng.standard_normal((n,) + tuple(crop) + (C,), dtype=np.float32)
+    return image, boxes, box_index, grads
+
+
+CAR_CASES = [
+    # B, H, W, D, C, n, crop
+    (2, 8, 8, 16, 64, 24, (7, 7, 7)),
+    (2, 8, 8, 16, 256, 12, (14, 14, 14)),
+    (1, 16, 16, 32, 32, 16, (7, 7, 7)),
+    (2, 6, 7, 9, 8, 10, (3, 4, 5)),
+    (2, 5, 4, 6, 12, 8, (1, 2, 1)),
+    (1, 4, 4, 8, 128, 8, (28, 28, 28)),
+    (3, 9, 5, 7, 1, 9, (5, 3, 4)),                            # C = 1 (mask targets, core/models.py:992)
+    (2, 7, 6, 5, 3, 9, (2, 2, 2)),                            # C % 4 != 0
+    (1, 32, 32, 16, 64, 6, (14, 14, 14)),                     # large footprints -> several y-tiles
+    (1, 2, 2, 2, 4, 7, (64, 3, 2)),
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("case", CAR_CASES)
+def test_car_forward_matches_oracle(rb, cuda_device, case, variant):
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, _ = car_inputs(100 + C + n, B, H, W, D, C, n, crop)
+    rb.custom_op.set_option("car_fwd_variant", variant)
+    out = rb.crop_and_resize_3d(dev(image, cuda_device), dev(boxes, cuda_device), dev(bidx, cuda_device), crop,
+                                extrapolation_value=0.5).cpu().numpy()
+    ref = oracle.crop_and_resize_3d(image, boxes, bidx, crop, "trilinear", 0.5)
+    assert out.shape == ref.shape
+    assert rel_ok(out, ref, FWD_TOL)
+    assert np.array_equal(out, ref)                             # same operations, same order: bit-exact
+
+
+@pytest.mark.parametrize("case", CAR_CASES[:5] + CAR_CASES[6:8])
+def test_car_forward_nearest(rb, cuda_device, case):
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, _ = car_inputs(200 + C + n, B, H, W, D, C, n, crop)
+    out = rb.crop_and_resize_3d(dev(image, cuda_device), dev(boxes, cuda_device), dev(bidx, cuda_device), crop,
+                                method_name="nearest", extrapolation_value=-1.0).cpu().numpy()
+    assert np.array_equal(out, oracle.crop_and_resize_3d(image, boxes, bidx, crop, "nearest", -1.0))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("case", CAR_CASES)
+def test_car_grad_image_matches_oracle(rb, cuda_device, case, variant):
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, grads = car_inputs(300 + C + n, B, H, W, D, C, n, crop)
+    rb.custom_op.set_option("car_bwd_variant", variant)
+    out = rb.crop_and_resize_3d_grad_image(dev(grads, cuda_device), dev(boxes, cuda_device), dev(bidx, cuda_device),
+                                           image.shape).cpu().numpy()
+    ref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape)
+    assert out.shape == ref.shape
+    assert rel_ok(out, ref, BWD_TOL)
+
+
+@pytest.mark.parametrize("case", CAR_CASES[:5] + CAR_CASES[6:8])
+def test_car_grad_image_nearest(rb, cuda_device, case):
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, grads = car_inputs(400 + C + n, B, H, W, D, C, n, crop)
+    out = rb.crop_and_resize_3d_grad_image(dev(grads, cuda_device), dev(boxes, cuda_device), dev(bidx, cuda_device),
+                                           image.shape, method_name="nearest").cpu().numpy()
+    assert rel_ok(out, oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape, "nearest"), BWD_TOL)
+
+
+@pytest.mark.parametrize("case", CAR_CASES[:5] + CAR_CASES[6:8])
+def test_car_grad_boxes_matches_oracle(rb, cuda_device, case):
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, grads = car_inputs(500 + C + n, B, H, W, D, C, n, crop)
+    out = rb.crop_and_resize_3d_grad_boxes(dev(grads, cuda_device), dev(image, cuda_device), dev(boxes, cuda_device),
+                                           dev(bidx, cuda_device)).cpu().numpy()
+    ref = oracle.crop_and_resize_3d_grad_boxes(grads, image, boxes, bidx)
+    # the reference accumulates ~1e5 fp32 terms sequentially; compare at the accuracy of that sum
+    assert np.all(np.abs(out - ref) <= GB_TOL * np.abs(ref).max() + 1e-6)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "car_*.npz"))))
+def test_car_golden(rb, cuda_device, path):
+    z = np.load(path)
+    crop = tuple(int(v) for v in z["crop"])
+    image, boxes, bidx, grads = (dev(z[k], cuda_device) for k in ("image", "boxes", "box_index", "grads"))
+    for method in ("trilinear", "nearest"):
+        out = rb.crop_and_resize_3d(image, boxes, bidx, crop, method_name=method, extrapolation_value=0.25)
+        assert np.array_equal(out.cpu().numpy(), z["fwd_" + method])
+        gi = rb.crop_and_resize_3d_grad_image(grads, boxes, bidx, z["image"].shape, method_name=method)
+        assert rel_ok(gi.cpu().numpy(), z["gi_" + method], BWD_TOL)
+    gb = rb.crop_and_resize_3d_grad_boxes(grads, image, boxes, bidx).cpu().numpy()
+    assert np.all(np.abs(gb - z["gb"]) <= GB_TOL * np.abs(z["gb"]).max() + 1e-6)
+
+
+def test_car_empty_and_single(rb, cuda_device):
+    import torch
+    image = dev(np.ones((1, 4, 4, 4, 8), np.float32), cuda_device)
+    e6 = torch.zeros((0, 6), device=cuda_device)
+    ei = torch.zeros((0,), dtype=torch.int32, device=cuda_device)
+    assert tuple(rb.crop_and_resize_3d(image, e6, ei, (7, 7, 7)).shape) == (0, 7, 7, 7, 8)
+    g = torch.zeros((0, 7, 7, 7, 8), device=cuda_device)
+    gi = rb.crop_and_resize_3d_grad_image(g, e6, ei, (1, 4, 4, 4, 8))
+    assert tuple(gi.shape) == (1, 4, 4, 4, 8) and float(gi.abs().sum()) == 0.0     # zero-filled like GI.so@0x3ec5
+    assert tuple(rb.crop_and_resize_3d_grad_boxes(g, image, e6, ei).shape) == (0, 6)
+
+
+def test_autograd_matches_registered_gradient(rb, cuda_device):
+    """backward() == (CropAndResize3DGradImage, CropAndResize3DGradBoxes, None, None) -- the wiring of
+    _CropAndResize3DGrad, core/custom_op/custom_op.py:28-65."""
+    B, H, W, D, C, n, crop = 2, 8, 8, 12, 16, 10, (5, 5, 5)
+    image, boxes, bidx, grads = car_inputs(600, B, H, W, D, C, n, crop)
+    t_img = dev(image, cuda_device).requires_grad_(True)
+    t_box = dev(boxes, cuda_device).requires_grad_(True)
+    out = rb.crop_and_resize_3d(t_img, t_box, dev(bidx, cuda_device), crop)
+    out.backward(dev(grads, cuda_device))
+    assert rel_ok(t_img.grad.cpu().numpy(), oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape), BWD_TOL)
+    ref = oracle.crop_and_resize_3d_grad_boxes(grads, image, boxes, bidx)
+    assert np.all(np.abs(t_box.grad.cpu().numpy() - ref) <= GB_TOL * np.abs(ref).max())
+
+
+def test_host_buffers_round_trip(rb, cuda_device):
+    """numpy in -> numpy out through pinned H2D/D2H: the end-to-end path bench.py times."""
+    B, H, W, D, C, n, crop = 2, 8, 8, 16, 64, 12, (7, 7, 7)
+    image, boxes, bidx, grads = car_inputs(700, B, H, W, D, C, n, crop)
+    out = rb.crop_and_resize_3d(image, boxes, bidx, crop)
+    assert isinstance(out, np.ndarray) and np.array_equal(out, oracle.crop_and_resize_3d(image, boxes, bidx, crop))
+    gi = rb.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape)
+    assert isinstance(gi, np.ndarray) and rel_ok(gi, oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape), BWD_TOL)
+    bx, sc = roi3d_synth.nms_boxes(800, (64, 64, 64), seed=5)
+    keep = rb.non_max_suppression_3d(bx, sc, 100, 0.5)
+    assert isinstance(keep, np.ndarray) and np.array_equal(keep, oracle.non_max_suppression_3d(bx, sc, 100, 0.5))
+
+
+# =============================================================================================
+# BASELINE shapes (cfg2: B=2, 128^3, 128 ROIs/image, C=256, P2..P5) -- size-independent properties
+# =============================================================================================
+@pytest.mark.parametrize("crop", [(7, 7, 7), (14, 14, 14)])
+def test_cfg2_full_size_properties(rb, cuda_device, crop):
+    import torch
+    vol, B = (128, 128, 128), 2
+    routed = roi3d_synth.pyramid_rois(128, B, vol, seed=2002)
+    assert sum(len(v[0]) for v in routed.values()) == 256
+    for level, (boxes, bidx, _) in routed.items():
+        if len(boxes) == 0:
+            continue
+        shape = roi3d_synth.level_shape(vol, level, batch=B)
+        torch.manual_seed(1000 + level)
+        image = torch.randn(shape, device=cuda_device)
+        tb, ti = dev(boxes, cuda_device), dev(bidx, cuda_device)
+        rb.custom_op.set_option("car_fwd_variant", 2)
+        out2 = rb.crop_and_resize_3d(image, tb, ti, crop)
+        rb.custom_op.set_option("car_fwd_variant", 1)
+        out1 = rb.crop_and_resize_3d(image, tb, ti, crop)
+        assert torch.equal(out1, out2)                          # direct gather == plane-staged, bit for bit
+        # a handful of ROIs against the oracle at full feature-map size
+        pick = np.arange(0, len(boxes), max(1, len(boxes) // 4))[:4]
+        ref = oracle.crop_and_resize_3d(image.cpu().numpy(), boxes[pick], bidx[pick], crop)
+        assert np.array_equal(out2[torch.from_numpy(pick).to(cuda_device)].cpu().numpy(), ref)
+        # adjoint identity <fwd(image), g> == <image, bwd(g)> ties backward to forward at full size
+        g = torch.randn_like(out2)
+        for variant in (1, 2):
+            rb.custom_op.set_option("car_bwd_variant", variant)
+            gi = rb.crop_and_resize_3d_grad_image(g, tb, ti, shape)
+            lhs = float((out2.double() * g.double()).sum())
+            rhs = float((image.double() * gi.double()).sum())
+            assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), float(out2.double().norm() * g.double().norm()) * 1e-3)
+        # linearity of the backward: bwd(2g) == 2 bwd(g) up to atomic re-ordering
+        gi2 = rb.crop_and_resize_3d_grad_image(2 * g, tb, ti, shape)
+        assert torch.allclose(gi2, 2 * gi, rtol=1e-4, atol=1e-4 * float(gi.abs().max()))
+        del image, out1, out2, g, gi, gi2
+        torch.cuda.empty_cache()
