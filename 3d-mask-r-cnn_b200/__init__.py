@@ -24,7 +24,11 @@ from .custom_op import (        # noqa: E402,F401
     crop_and_resize_3d,
     crop_and_resize_3d_grad_boxes,
     crop_and_resize_3d_grad_image,
+    get_option,
+    kernel_launches,
     non_max_suppression_3d,
+    reset_kernel_launches,
+    set_option,
 )
 
 __version__ = "0.1.0"

@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ROI hot path (BASELINE.json metric:
+"3D ROIAlign fwd+bwd ROIs/s & HBM GB/s; NMS3D ms @6k boxes; 1/2/4/8 B200").
+
+Workload (config.workload = "cfg2", BASELINE.json configs[1]): training_head_e2e step, batch 2 of
+128^3 volumes, TRAIN_ROIS_PER_IMAGE=128 -> 256 ROIs routed over P2..P5 (C=256, this fork's (2,2,1)
+strides), CropAndResize3D forward + grad-image for the classifier (7^3) and mask (14^3) heads:
+per step up to 8 forward ops and 8 grad-image ops.  One "ROI" of the metric is one ROI taken through
+all four (7^3 fwd, 14^3 fwd, 7^3 bwd, 14^3 bwd).
+
+  value   ROIs/s with every input already resident in HBM (C-ABI calls on device pointers).
+  e2e     ROIs/s through the public host-buffer API (pinned numpy/CPU tensors in, host results out):
+          H2D of feature maps / boxes / grads and D2H of crops / grad images inside the timed region.
+  N > 1   one process per GPU (torchrun), every rank runs its own batch (images never share ROIs, no
+          collective on the data path): weak scaling, value = N * ROIs / max-over-ranks time.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port of the
+wheel's kernels, all host cores) on the same config.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import roi3d_synth  # noqa: E402
+
+VOLUME = (128, 128, 128)
+BATCH = 2
+ROIS_PER_IMAGE = 128
+CROPS = ((7, 7, 7), (14, 14, 14))
+METRIC = "3D ROIAlign fwd+bwd ROIs/s"
+UNIT = "ROIs/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def make_workload(seed=2002, with_data=True):
+    routed = roi3d_synth.pyramid_rois(ROIS_PER_IMAGE, BATCH, VOLUME, seed=seed)
+    ops = []
+    for level in roi3d_synth.LEVELS:
+        boxes, bidx, _ = routed[level]
+        shape = roi3d_synth.level_shape(VOLUME, level, batch=BATCH)
+        image = roi3d_synth.feature_map(VOLUME, level, batch=BATCH) if with_data else None
+        for crop in CROPS:
+            n = len(boxes)
+            ops.append({
+                "level": level, "crop": crop, "n": n, "shape": shape, "image": image,
+                "boxes": boxes, "bidx": bidx,
+                "grads": roi3d_synth.grads_like((n,) + crop + (shape[4],), 4000 + level * 10 + crop[0])
+                if with_data else None,
+                "fwd_bytes": roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=False) if n else 0,
+                "bwd_bytes": roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=True),
+            })
+    return ops
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import roi3d_b200 as rb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = rb._lib.load()
+    vp = ctypes.c_void_p
+    stream = lambda: vp(torch.cuda.current_stream().cuda_stream)   # noqa: E731
+
+    ops = make_workload(seed=2002 + rank)
+    total_rois = BATCH * ROIS_PER_IMAGE
+    # ---- device-resident state ---------------------------------------------------------------
+    images = {}
+    for op in ops:
+        lv = op["level"]
+        if lv not in images:
+            images[lv] = torch.from_numpy(op["image"]).to(dev)
+        op["d_image"] = images[lv]
+        op["d_boxes"] = torch.from_numpy(op["boxes"]).to(dev)
+        op["d_bidx"] = torch.from_numpy(op["bidx"]).to(dev)
+        op["d_grads"] = torch.from_numpy(op["grads"]).to(dev)
+        op["d_crops"] = torch.empty_like(op["d_grads"])
+        op["d_gimg"] = torch.empty(op["shape"], dtype=torch.float32, device=dev)
+
+    def ptr(t):
+        return vp(t.data_ptr() if t.numel() else 0)
+
+    def fwd(op):
+        B, H, W, D, C = op["shape"]
+        c = op["crop"]
+        rb._lib.check(lib.roi3d_car3d_fwd(ptr(op["d_image"]), B, H, W, D, C, ptr(op["d_boxes"]), ptr(op["d_bidx"]),
+                                          op["n"], c[0], c[1], c[2], 0, 0.0, ptr(op["d_crops"]), stream()))
+
+    def bwd(op):
+        B, H, W, D, C = op["shape"]
+        c = op["crop"]
+        rb._lib.check(lib.roi3d_car3d_grad_image(ptr(op["d_grads"]), ptr(op["d_boxes"]), ptr(op["d_bidx"]), op["n"],
+                                                 c[0], c[1], c[2], B, H, W, D, C, 0, ptr(op["d_gimg"]), stream()))
+
+    def step():
+        for op in ops:
+            fwd(op)
+        for op in ops:
+            bwd(op)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    rb.reset_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = rb.kernel_launches()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / args.steps
+    value = world * total_rois / (ms_step * 1e-3)
+
+    # ---- per-op timing (CUDA events on the launching stream) -> roofline of the dominant kernel ----
+    peak, peak_src = load_peaks()
+    per_op = []
+    reps = max(args.steps, 5)
+    for kind, fn in (("fwd", fwd), ("bwd", bwd)):
+        for op in ops:
+            evs = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(op)
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+            nbytes = op[kind + "_bytes"]
+            per_op.append({"op": "car3d_" + ("fwd" if kind == "fwd" else "grad_image"), "level": op["level"],
+                           "crop": op["crop"][0], "n": op["n"], "ms": round(ms, 4), "alg_bytes": nbytes,
+                           "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None})
+    dom = max(per_op, key=lambda r: r["ms"])
+    roofline = {"bound": "hbm", "kernel": "%s P%d crop %d^3 n=%d" % (dom["op"], dom["level"], dom["crop"], dom["n"]),
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration of the C-ABI call"
+                        + (" (zero-fill memset + scatter kernel)" if dom["op"].endswith("grad_image") else "")}
+    sum_bytes = sum(r["alg_bytes"] for r in per_op)
+    step_gbs = sum_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- NMS3D @6k boxes (cfg1: 6000 -> 1000 @0.7), device resident and host-buffer end to end ----
+    nb, ns = roi3d_synth.nms_boxes(6000, VOLUME)
+    d_nb, d_ns = torch.from_numpy(nb).to(dev), torch.from_numpy(ns).to(dev)
+    wsb = lib.roi3d_nms3d_workspace_bytes(6000)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    keep = torch.empty(1000, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    nms_ms = []
+    for it in range(60):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rb._lib.check(lib.roi3d_nms3d(ptr(d_nb), ptr(d_ns), 6000, 1000, 0.7, ptr(keep), ptr(cnt), ptr(ws), wsb, stream()))
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 10:
+            nms_ms.append(a.elapsed_time(b))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        kept = rb.non_max_suppression_3d(nb, ns, 1000, 0.7)
+    nms_e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    nms = {"boxes": 6000, "max_out": 1000, "iou_threshold": 0.7, "kept": int(cnt.item()),
+           "ms": round(statistics.median(nms_ms), 4), "ms_p10": round(sorted(nms_ms)[len(nms_ms) // 10], 4),
+           "ms_p90": round(sorted(nms_ms)[len(nms_ms) * 9 // 10], 4),
+           "boxes_per_s": round(6000 / (statistics.median(nms_ms) * 1e-3)),
+           "e2e_host_buffers_ms": round(nms_e2e_ms, 4), "e2e_kept": int(len(kept))}
+
+    # ---- end to end through the public API with host buffers ---------------------------------------
+    h_images = {lv: torch.from_numpy(op["image"]).pin_memory() for lv, op in ((o["level"], o) for o in ops)}
+    h = [{"boxes": torch.from_numpy(op["boxes"]), "bidx": torch.from_numpy(op["bidx"]),
+          "grads": torch.from_numpy(op["grads"]).pin_memory()} for op in ops]
+    h2d = sum(t.numel() * 4 for t in h_images.values()) * len(CROPS) + sum(x["grads"].numel() * 4 for x in h) + \
+        2 * sum(x["boxes"].numel() * 4 + x["bidx"].numel() * 4 for x in h)
+    d2h = sum(x["grads"].numel() * 4 for x in h) + sum(int(np.prod(op["shape"])) * 4 for op in ops)
+
+    def e2e_step():
+        outs = []
+        for op, x in zip(ops, h):
+            outs.append(rb.crop_and_resize_3d(h_images[op["level"]], x["boxes"], x["bidx"], op["crop"]))
+        for op, x in zip(ops, h):
+            outs.append(rb.crop_and_resize_3d_grad_image(x["grads"], x["boxes"], x["bidx"], op["shape"]))
+        return outs
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = world * total_rois * e2e_steps / e2e_s
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: batch 2 x 128^3, 128 ROIs/image, P2-P5 C=256, CropAndResize3D fwd + grad-image "
+                               "for 7^3 and 14^3 heads (16 op calls/step)",
+                   "rois_per_step_per_gpu": total_rois, "l2": "inputs larger than L2 (feature maps 356 MB + grads "
+                   "809 MB per step; no explicit flush)", "sharding": "one batch per GPU, no collective"},
+        "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
+        "roofline": roofline,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "nms3d": nms,
+        "ops": per_op,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(ops, threads=None)
+        line["cpu_baseline_1thread"] = cpu_baseline(ops, threads=1, sample_rois=32)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference kernels (test infrastructure, never the product)
+# ------------------------------------------------------------------------------------------
+def cpu_step(ops, threads, sample_rois):
+    """One step on the host over the first `sample_rois` ROIs of every op; returns (seconds, rois, fill_s)."""
+    import oracle
+    t_all, t_fill, done = 0.0, 0.0, 0
+    frac = min(1.0, sample_rois / float(BATCH * ROIS_PER_IMAGE))
+    for op in ops:
+        n = int(round(op["n"] * frac)) if op["n"] else 0
+        n = max(n, 1) if op["n"] else 0
+        bx, bi, g = op["boxes"][:n], op["bidx"][:n], op["grads"][:n]
+        t0 = time.perf_counter()
+        oracle.crop_and_resize_3d(op["image"], bx, bi, op["crop"], threads=threads)
+        t1 = time.perf_counter()
+        oracle.crop_and_resize_3d_grad_image(g, bx, bi, op["shape"], threads=threads)
+        t2 = time.perf_counter()
+        oracle.crop_and_resize_3d_grad_image(g[:0], bx[:0], bi[:0], op["shape"], threads=threads)   # zero-fill only
+        t3 = time.perf_counter()
+        t_all += t2 - t0
+        t_fill += t3 - t2
+        if op["crop"] == CROPS[0]:
+            done += n
+    return t_all, done, t_fill
+
+
+def cpu_baseline(ops, threads=None, sample_rois=64):
+    import oracle
+    threads = threads or oracle.max_threads()
+    total = BATCH * ROIS_PER_IMAGE
+    t_all, done, t_fill = cpu_step(ops, threads, sample_rois)
+    # per-ROI work scales with the ROI count, the zero-fill of the 8 grad images is paid once per step
+    t_step = t_fill + (t_all - t_fill) * total / max(done, 1)
+    return {"value": round(total / t_step, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d of %d ROIs through all 16 ops on full-size feature maps (%.1f s of CPU work); step time "
+                      "extrapolated as zero-fill + per-ROI time x 256" % (done, total, t_all),
+            "ms_per_step": round(t_step * 1e3, 1)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the step (oracle port of the wheel's kernels; the binaries
+    themselves need TF 2.2 / cp36 and cannot run), all host threads, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    ops = make_workload(seed=2002)
+    threads = oracle.max_threads()
+    total = BATCH * ROIS_PER_IMAGE
+    sample = 64
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(ops, threads, 8)
+    t_sum, vals = 0.0, []
+    for _ in range(args.steps):
+        t_all, done, t_fill = cpu_step(ops, threads, sample)
+        t_step = t_fill + (t_all - t_fill) * total / max(done, 1)
+        vals.append(t_step)
+        t_sum += t_all
+        if t_sum > 150:
+            break
+    t_step = statistics.mean(vals)
+    value = round(total / t_step, 3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": min(args.warmup, 1), "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: batch 2 x 128^3, 128 ROIs/image, P2-P5 C=256, CropAndResize3D fwd + grad-image "
+                               "for 7^3 and 14^3 heads (16 op calls/step)", "rois_per_step_per_gpu": total},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d of %d ROIs per step through all 16 ops, full-size feature maps; step time = "
+                                   "zero-fill + per-ROI time x 256; OpenMP over boxes (fwd) / channels (bwd)" % (sample, total)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
