@@ -264,13 +264,16 @@ def run_ours(args):
         return outs
 
     e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.no_e2e:
+        e2e_steps, e2e_s = 1, float("inf")
+    else:
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -386,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
