@@ -16,6 +16,7 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_fwd_variant")) return OPT_CAR_FWD_VARIANT;
     if (!strcmp(name, "car_bwd_variant")) return OPT_CAR_BWD_VARIANT;
     if (!strcmp(name, "nms_variant")) return OPT_NMS_VARIANT;
+    if (!strcmp(name, "car_lanes_v")) return OPT_CAR_V;
     return -1;
 }
 
@@ -91,7 +92,9 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
     int variant = option_value(OPT_CAR_FWD_VARIANT);
     const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
                           ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(crops)) & 15) == 0;
-    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
+    // measured on B200 (profiles/variants_r1.txt): the plane-staged kernel wins once a depth slice has
+    // enough outputs to amortise its per-CTA tables (14^3: 2.1x), the direct gather wins at 7^3
+    if (variant == 0) variant = (plane_ok && C >= 32 && ph * pw >= 100) ? 2 : 1;
     if (variant == 2 && plane_ok) return launch_car3d_fwd_plane(image, boxes, box_index, g, extrapolation_value, crops, s);
     return launch_car3d_fwd_direct(image, boxes, box_index, g, method, extrapolation_value, crops, s);
 }

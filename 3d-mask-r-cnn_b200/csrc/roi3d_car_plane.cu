@@ -4,7 +4,7 @@
 // Why: trilinear taps form a product set.  For one ROI and one depth sample k the
 // reference (CAR.so@0x4f88-0x5021) first lerps along z, then x, then y, each as
 // a + (b - a) * t.  The z-lerp of a voxel column (yi, xi) depends only on (yi, xi, k),
-// so a CTA that owns (ROI, k-range, 64-channel chunk)
+// so a CTA that owns (ROI, k-range, channel chunk)
 //   A. reads every footprint voxel (yi, xi, {floor z, ceil z}) exactly ONCE from global
 //      memory (coalesced 16-byte loads along channels), z-lerps it in registers and
 //      parks the result in a shared-memory plane Z[row][col][chunk];
@@ -14,23 +14,23 @@
 // order and rounding, so the result is bit-identical to the direct kernel and to the
 // oracle, while L2->SM traffic drops from 8 taps per output to 2 * footprint / outputs.
 //
-// Instruction economy (round-1 ncu: the first version issued ~190 warp instructions per
-// 16-byte output and was issue-bound at 47 % of HBM): everything that depends only on
+// Instruction economy (profiles/r1a, r1b: the first versions issued 190 / 134 warp
+// instructions per 16-byte output and were issue-bound): everything that depends only on
 // (ROI, y-tile) -- footprint voxel offsets, and per output the four plane offsets plus the
-// x/y lerp weights -- is tabulated once per CTA in shared memory, so the k loop does one
-// table read, four plane reads, the 36 exactly-rounded fp32 ops and one store per output.
+// x/y lerp weights -- is tabulated once per CTA in shared memory; each thread carries V
+// float4 channel groups through every index computation; shared memory is addressed with
+// 32-bit shared-window addresses; out-of-range outputs are selected, not branched.
 //
 // The backward kernel is the transpose: the k-slice of grads is staged in shared memory
 // (each element read once, coalesced), every footprint voxel gathers its (wy*wx)-weighted
-// sum from that slice (deterministic, no shared-memory atomics) and issues two vector REDs
-// (floor z, ceil z) instead of 8 per grads element.
+// sum over per-axis contribution lists (deterministic order, no shared-memory atomics)
+// and issues two vector REDs (floor z, ceil z) instead of 8 per grads element.
 #include "roi3d_common.cuh"
 
 namespace roi3d {
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_MAXP = 64;                 // max crop size per axis handled here
-constexpr int PL_UNROLL = 4;
 constexpr int PL_MAXOUT = 1024;             // output-table entries per y-tile
 
 struct AxisTab {                            // one per axis (y, x), lives in shared memory
@@ -134,7 +134,7 @@ __device__ __forceinline__ void build_y_tiles(PlaneShared &S, const CarGeom &g, 
 }
 
 struct PlaneLaunch {
-    int cl;            // channel lanes (float4 each) per voxel
+    int cl;            // channel lanes per voxel (each lane carries V float4 groups)
     int chunks;        // channel chunks per voxel
     int ksplits;       // depth-sample splits per ROI
     int zcap;          // plane capacity in voxels (forward) / staged grads entries (backward)
@@ -147,14 +147,20 @@ struct __align__(16) OutEntry {             // per output (y, x) of the current 
     float xl, yl;
 };
 
+__device__ __forceinline__ float4 sel4(bool bad, const float4 a, const float4 b) {
+    return make_float4(bad ? a.x : b.x, bad ? a.y : b.y, bad ? a.z : b.z, bad ? a.w : b.w);
+}
+
 // ---------------------------------------------------------------------------------
-// forward
+// forward.  V = float4 channel groups per thread (the chunk is cl * V * 4 channels).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PL_THREADS, 4)
+template <int V>
+__global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                        const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
                        float *__restrict__ crops)
 {
+    constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
     PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
@@ -175,8 +181,10 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const int nx = X.n;
     const int cl = L.cl;
     const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
-    const int c4 = chunk * cl + lane;                       // float4 channel group
-    const bool lane_on = c4 < g.C / 4;
+    const int c4 = chunk * cl * V + lane;                   // first float4 channel group of this thread
+    bool von[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
     const float *img = image + (long long)__ldg(box_index + b) * g.H * sH + c4 * 4;
     float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
@@ -185,10 +193,11 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const float zscale = axis_scale(z1, z2, g.D, g.pd);
     const int kper = (g.pd + L.ksplits - 1) / L.ksplits;
     const int k0 = ks * kper, k1 = min(g.pd, k0 + kper);
-    float4 *Zst = reinterpret_cast<float4 *>(Zraw) + lane;   // stage-A store base
-    const unsigned char *Zld = Zraw + lane * 16;               // stage-B load base
-    const unsigned ebytes = (unsigned)cl * 16;                 // bytes per plane voxel
+    const unsigned ebytes = (unsigned)cl * V * 16;             // bytes per plane voxel
+    const unsigned z_u32 = smem_u32(Zraw) + lane * 16;         // this lane's column of the plane
+    const unsigned otab_u32 = smem_u32(otab), voff_u32 = smem_u32(voff);
     const long long ostride = (long long)vs * g.pd * g.C;
+    const int vstep = cl * 4;                                  // floats between a thread's channel groups
 
     for (int tl = 0; tl < S.ntiles; ++tl) {
         const int ya = S.tile_y0[tl], yb = S.tile_y0[tl + 1];
@@ -220,48 +229,61 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
         for (int k = k0; k < k1; ++k) {
             const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
             float *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
-            if (axis_invalid(in_z, g.D)) {                   // uniform: the whole depth sample extrapolates
-                if (lane_on)
-                    for (int idx = slot; idx < nout; idx += vs, o += ostride) st_stream4(o, ext4);
+            if (axis_invalid(in_z, g.D) || nvox == 0) {       // uniform: every output of this (tile, k) extrapolates
+                for (int idx = slot; idx < nout; idx += vs, o += ostride) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (von[v]) st_stream4(o + v * vstep, ext4);
+                }
                 continue;
             }
             const float zfl = floorf(in_z);
             const unsigned zf = (unsigned)(int)zfl * g.C, zc = (unsigned)(int)ceilf(in_z) * g.C;
             const float zl = __fsub_rn(in_z, zfl);
             // ---- stage A: footprint voxels -> z-lerp -> shared plane ----------------
-            if (lane_on) {
-                for (int base = slot; base < nvox; base += vs * PL_UNROLL) {
-                    float4 f[PL_UNROLL], c[PL_UNROLL];
+            for (int base = slot; base < nvox; base += vs * UNR) {
+                float4 f[UNR][V], c[UNR][V];
 #pragma unroll
-                    for (int u = 0; u < PL_UNROLL; ++u) {
-                        const int idx = base + u * vs;
-                        if (idx < nvox) {
-                            const float *p = img + voff[idx];
-                            f[u] = ldg4(p + zf);
-                            c[u] = ldg4(p + zc);
+                for (int u = 0; u < UNR; ++u) {
+                    const int idx = min(base + u * vs, nvox - 1);      // clamp: tail lanes re-read a valid voxel
+                    const float *p = img + lds32u(voff_u32 + idx * 4);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if (von[v]) {
+                            f[u][v] = ldg4(p + zf + v * vstep);
+                            c[u][v] = ldg4(p + zc + v * vstep);
                         }
                     }
+                }
 #pragma unroll
-                    for (int u = 0; u < PL_UNROLL; ++u) {
-                        const int idx = base + u * vs;
-                        if (idx < nvox) Zst[idx * cl] = lerp_rn(f[u], c[u], zl);
+                for (int u = 0; u < UNR; ++u) {
+                    const int idx = base + u * vs;
+                    if (idx < nvox) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            if (von[v]) sts128(z_u32 + idx * ebytes + v * (cl * 16), lerp_rn(f[u][v], c[u][v], zl));
                     }
                 }
             }
             __syncthreads();
             // ---- stage B: x-lerp, y-lerp from the plane -> crops ----------------------
-            if (lane_on) {
 #pragma unroll 2
-                for (int idx = slot; idx < nout; idx += vs, o += ostride) {
-                    const uint4 e = *reinterpret_cast<const uint4 *>(&otab[idx]);
-                    if (e.x == 0xFFFFFFFFu) { st_stream4(o, ext4); continue; }
-                    const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
-                    const float4 tlv = *reinterpret_cast<const float4 *>(Zld + (e.x & 0xFFFFu));
-                    const float4 trv = *reinterpret_cast<const float4 *>(Zld + (e.x >> 16));
-                    const float4 blv = *reinterpret_cast<const float4 *>(Zld + (e.y & 0xFFFFu));
-                    const float4 brv = *reinterpret_cast<const float4 *>(Zld + (e.y >> 16));
-                    const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
-                    st_stream4(o, lerp_rn(top, bot, yl));
+            for (int idx = slot; idx < nout; idx += vs, o += ostride) {
+                const uint4 e = lds128u(otab_u32 + idx * 16);
+                const bool bad = e.x == 0xFFFFFFFFu;
+                const unsigned et = bad ? 0u : e.x, eb = bad ? 0u : e.y;
+                const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
+                const unsigned a_tl = z_u32 + (et & 0xFFFFu), a_tr = z_u32 + (et >> 16);
+                const unsigned a_bl = z_u32 + (eb & 0xFFFFu), a_br = z_u32 + (eb >> 16);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (von[v]) {
+                        const unsigned vo = v * (cl * 16);
+                        const float4 tlv = lds128(a_tl + vo), trv = lds128(a_tr + vo);
+                        const float4 blv = lds128(a_bl + vo), brv = lds128(a_br + vo);
+                        const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
+                        st_stream4(o + v * vstep, sel4(bad, ext4, lerp_rn(top, bot, yl)));
+                    }
                 }
             }
             __syncthreads();
@@ -272,43 +294,62 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
 // ---------------------------------------------------------------------------------
 // backward (grad image).  grad_image must be zero-filled before the launch.
 // ---------------------------------------------------------------------------------
-struct BwdRanges {                          // per footprint position: the samples that tap it
-    short a0[2 * PL_MAXP], e0[2 * PL_MAXP]; // [a0,e0): samples whose floor is this position
-    short a1[2 * PL_MAXP], e1[2 * PL_MAXP]; // [a1,e1): samples whose ceil is this position
+struct __align__(8) Contrib { unsigned off; float w; };   // staged-slice byte offset of a sample, its weight
+
+struct BwdLists {
+    short start[2][2 * PL_MAXP];            // per axis, per footprint position: first entry ...
+    short cnt[2][2 * PL_MAXP];              // ... and number of entries
+    short samp[2][2 * PL_MAXP];             // sample index of each entry
+    Contrib ent[2][2 * PL_MAXP];            // (offset, weight) of each entry
 };
 
-__device__ __forceinline__ void build_ranges(const AxisTab &T, BwdRanges &R, int p, int tid0, int nthreads)
+// Contribution lists: footprint position q of axis a is tapped by the samples whose floor is q
+// (weight 1 - t) and by those whose ceil is q (weight t); both sets are contiguous sample ranges
+// because `in` is monotonic in the sample index.
+__device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, const CarGeom &g, unsigned ebytes)
 {
-    // samples with a given floor (ceil) position are contiguous because `in` is monotonic in the sample index
-    for (int q = tid0; q < T.n; q += nthreads) {
-        int a0 = p, e0 = 0, a1 = p, e1 = 0;
-        for (int s = 0; s < p; ++s) {
-            if (T.pos0[s] == q) { a0 = min(a0, s); e0 = max(e0, s + 1); }
-            if (T.pos1[s] == q) { a1 = min(a1, s); e1 = max(e1, s + 1); }
+    const int tid = threadIdx.x;
+    if (tid < 2) {                                             // thread a: prefix of the counts of axis a
+        const AxisTab &T = S.ax[tid];
+        const int p = tid ? g.pw : g.ph;
+        int run = 0;
+        for (int q = 0; q < T.n; ++q) {
+            int c = 0;
+            for (int s = 0; s < p; ++s) c += (T.pos0[s] == q) + (T.pos1[s] == q);
+            B.start[tid][q] = (short)run;
+            B.cnt[tid][q] = (short)c;
+            run += c;
         }
-        if (a0 >= e0) a0 = e0 = 0;
-        if (a1 >= e1) a1 = e1 = 0;
-        R.a0[q] = (short)a0; R.e0[q] = (short)e0;
-        R.a1[q] = (short)a1; R.e1[q] = (short)e1;
     }
+    __syncthreads();
+    if (tid < 4 * PL_MAXP) {                                    // one thread per (axis, position)
+        const int a = tid / (2 * PL_MAXP), q = tid % (2 * PL_MAXP);
+        const AxisTab &T = S.ax[a];
+        const int p = a ? g.pw : g.ph;
+        if (q < T.n) {
+            int w = B.start[a][q];
+            const unsigned unit = a ? ebytes : ebytes * (unsigned)g.pw;
+            for (int s = 0; s < p; ++s)
+                if (T.pos0[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, __fsub_rn(1.0f, T.t[s])}; ++w; }
+            for (int s = 0; s < p; ++s)
+                if (T.pos1[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, T.t[s]}; ++w; }
+        }
+    }
+    __syncthreads();
 }
 
-__device__ __forceinline__ void fma4(float4 &acc, const float4 a, float w) {
-    acc.x = __fmaf_rn(a.x, w, acc.x); acc.y = __fmaf_rn(a.y, w, acc.y);
-    acc.z = __fmaf_rn(a.z, w, acc.z); acc.w = __fmaf_rn(a.w, w, acc.w);
-}
-
-__global__ void __launch_bounds__(PL_THREADS, 4)
+template <int V>
+__global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
                               float *__restrict__ grad_image)
 {
+    constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
     PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
-    BwdRanges &RY = *reinterpret_cast<BwdRanges *>(smem_raw + off); off += (sizeof(BwdRanges) + 15) & ~size_t(15);
-    BwdRanges &RX = *reinterpret_cast<BwdRanges *>(smem_raw + off); off += (sizeof(BwdRanges) + 15) & ~size_t(15);
-    float4 *G = reinterpret_cast<float4 *>(smem_raw + off);          // staged grads slice [(y-ya)*pw + x][cl]
+    BwdLists &B = *reinterpret_cast<BwdLists *>(smem_raw + off);  off += (sizeof(BwdLists) + 15) & ~size_t(15);
+    unsigned char *Graw = smem_raw + off;                          // staged grads slice [(y-ya)*pw + x][V][cl] float4
 
     int bid = blockIdx.x;
     const int chunk = bid % L.chunks; bid /= L.chunks;
@@ -318,16 +359,17 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     __syncthreads();
     build_axis_tables(S, g);
     const AxisTab &Y = S.ax[0], &X = S.ax[1];
-    build_ranges(Y, RY, g.ph, threadIdx.x, PL_THREADS);
-    build_ranges(X, RX, g.pw, threadIdx.x, PL_THREADS);
-    __syncthreads();
+    const int cl = L.cl;
+    const unsigned ebytes = (unsigned)cl * V * 16;
+    build_lists(S, B, g, ebytes);
 
     const int nx = X.n, ny = Y.n;
     if (nx == 0 || ny == 0) return;                           // no in-range sample: nothing to scatter
-    const int cl = L.cl;
     const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
-    const int c4 = chunk * cl + lane;
-    const bool lane_on = c4 < g.C / 4;
+    const int c4 = chunk * cl * V + lane;
+    bool von[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const long long sW = (long long)g.D * g.C, sH = (long long)g.W * g.D * g.C;
     float *img = grad_image + (long long)__ldg(box_ind + b) * g.H * sH + c4 * 4;
     const float *gcrop = grads + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
@@ -337,12 +379,24 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     const int k0 = ks * kper, k1 = min(g.pd, k0 + kper);
     const int ty = max(1, L.zcap / g.pw);                    // y samples per tile
     const long long gstride = (long long)vs * g.pd * g.C;
-    const int nvox = ny * nx;
     const float rnx = 1.0f / (float)nx;
+    const int vstep = cl * 4;
+    const unsigned g_u32 = smem_u32(Graw) + lane * 16;
+    const unsigned yent_u32 = smem_u32(&B.ent[0][0]), xent_u32 = smem_u32(&B.ent[1][0]);
 
     for (int ya = 0; ya < g.ph; ya += ty) {
         const int yb = min(g.ph, ya + ty);
         const int nent = (yb - ya) * g.pw;
+        const unsigned tile_off = (unsigned)ya * g.pw * ebytes;
+        int rlo = 1 << 30, rhi = -1;                           // footprint rows tapped by this tile's samples
+        for (int y = ya; y < yb; ++y) {
+            const int a = Y.pos0[y], c = Y.pos1[y];
+            if (a < 0) continue;
+            rlo = min(rlo, min(a, c));
+            rhi = max(rhi, max(a, c));
+        }
+        if (rhi < rlo) continue;
+        const int nvox = (rhi - rlo + 1) * nx;
         for (int k = k0; k < k1; ++k) {
             const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
             if (axis_invalid(in_z, g.D)) continue;             // uniform across the CTA
@@ -350,41 +404,68 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
             const long long zf = (long long)(int)zfl * g.C, zc = (long long)(int)ceilf(in_z) * g.C;
             const float zl = __fsub_rn(in_z, zfl), wzf = __fsub_rn(1.0f, zl);
             // ---- stage A': stage the k-slice of grads (each element read once) -------------
-            if (lane_on) {
+            {
                 const float *gp = gcrop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
-                for (int base = slot; base < nent; base += vs * PL_UNROLL) {
-                    float4 v[PL_UNROLL];
+                for (int base = slot; base < nent; base += vs * UNR, gp += UNR * gstride) {
+                    float4 val[UNR][V];
 #pragma unroll
-                    for (int u = 0; u < PL_UNROLL; ++u)
-                        if (base + u * vs < nent) v[u] = ldg4(gp + u * gstride);
+                    for (int u = 0; u < UNR; ++u) {
+                        if (base + u * vs < nent) {
 #pragma unroll
-                    for (int u = 0; u < PL_UNROLL; ++u)
-                        if (base + u * vs < nent) G[(base + u * vs) * cl + lane] = v[u];
-                    gp += PL_UNROLL * gstride;
+                            for (int v = 0; v < V; ++v)
+                                if (von[v]) val[u][v] = ldg4(gp + u * gstride + v * vstep);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        if (base + u * vs < nent) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v)
+                                if (von[v]) sts128(g_u32 + (base + u * vs) * ebytes + v * (cl * 16), val[u][v]);
+                        }
+                    }
                 }
             }
             __syncthreads();
             // ---- stage B': every footprint voxel gathers its weighted sum, then 2 REDs ------
-            if (lane_on) {
-                for (int idx = slot; idx < nvox; idx += vs) {
-                    const int r = (int)(((float)idx + 0.5f) * rnx), cx = idx - r * nx;
-                    const int ylo0 = max((int)RY.a0[r], ya), yhi0 = min((int)RY.e0[r], yb);
-                    const int ylo1 = max((int)RY.a1[r], ya), yhi1 = min((int)RY.e1[r], yb);
-                    if (ylo0 >= yhi0 && ylo1 >= yhi1) continue;
-                    const int xa0 = RX.a0[cx], xe0 = RX.e0[cx], xa1 = RX.a1[cx], xe1 = RX.e1[cx];
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int ylo = pass ? ylo1 : ylo0, yhi = pass ? yhi1 : yhi0;
-                        for (int y = ylo; y < yhi; ++y) {
-                            const float wy = pass ? Y.t[y] : __fsub_rn(1.0f, Y.t[y]);
-                            const float4 *row = G + ((y - ya) * g.pw) * cl + lane;
-                            for (int x = xa0; x < xe0; ++x) fma4(acc, row[x * cl], __fmul_rn(wy, __fsub_rn(1.0f, X.t[x])));
-                            for (int x = xa1; x < xe1; ++x) fma4(acc, row[x * cl], __fmul_rn(wy, X.t[x]));
+            for (int idx = slot; idx < nvox; idx += vs) {
+                const int rr = (int)(((float)idx + 0.5f) * rnx), cx = idx - rr * nx, r = rlo + rr;
+                const int ys = B.start[0][r], yn = B.cnt[0][r];
+                const int xs = B.start[1][cx], xn = B.cnt[1][cx];
+                float4 acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool any = false;
+#pragma unroll 1
+                for (int i = ys; i < ys + yn; ++i) {
+                    const int y = B.samp[0][i];
+                    if (y < ya || y >= yb) continue;
+                    any = true;
+                    const uint2 ye = lds64u(yent_u32 + i * 8);
+                    const unsigned row = g_u32 + ye.x - tile_off;
+                    const float wy = __uint_as_float(ye.y);
+#pragma unroll 1
+                    for (int j = xs; j < xs + xn; ++j) {
+                        const uint2 xe = lds64u(xent_u32 + j * 8);
+                        const float w = __fmul_rn(wy, __uint_as_float(xe.y));
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if (von[v]) {
+                                const float4 gv = lds128(row + xe.x + v * (cl * 16));
+                                acc[v].x = __fmaf_rn(gv.x, w, acc[v].x); acc[v].y = __fmaf_rn(gv.y, w, acc[v].y);
+                                acc[v].z = __fmaf_rn(gv.z, w, acc[v].z); acc[v].w = __fmaf_rn(gv.w, w, acc[v].w);
+                            }
                         }
                     }
-                    float *p = img + Y.list[r] * sH + X.list[cx] * sW;
-                    red_add4(p + zf, make_float4(acc.x * wzf, acc.y * wzf, acc.z * wzf, acc.w * wzf));
-                    red_add4(p + zc, make_float4(acc.x * zl, acc.y * zl, acc.z * zl, acc.w * zl));
+                }
+                if (!any) continue;
+                float *p = img + Y.list[r] * sH + X.list[cx] * sW;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (von[v]) {
+                        red_add4(p + zf + v * vstep, make_float4(acc[v].x * wzf, acc[v].y * wzf, acc[v].z * wzf, acc[v].w * wzf));
+                        red_add4(p + zc + v * vstep, make_float4(acc[v].x * zl, acc[v].y * zl, acc[v].z * zl, acc[v].w * zl));
+                    }
                 }
             }
             __syncthreads();
@@ -397,10 +478,14 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
 // ---------------------------------------------------------------------------------
 static inline size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
 
-static int pick_cl(const CarGeom &g, int pref_cl) {
-    int cl = pref_cl;
-    while (cl > 1 && cl / 2 >= g.C / 4) cl /= 2;               // do not idle half the lanes
-    return cl;
+// channel lanes: 16 lanes x V float4 per voxel; narrower when C is small so that no lane idles
+static void pick_lanes(const CarGeom &g, int &cl, int &V) {
+    const int c4 = g.C / 4;
+    V = (c4 >= 32) ? 2 : 1;
+    const int forced = option_value(OPT_CAR_V);
+    if (forced == 1 || forced == 2) V = forced;
+    cl = 16;
+    while (cl > 1 && cl / 2 * V >= c4) cl /= 2;
 }
 
 static int pick_ksplits(const CarGeom &g, int chunks) {
@@ -416,27 +501,28 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
                            float ext, float *crops, cudaStream_t stream)
 {
     PlaneLaunch L;
-    L.cl = pick_cl(g, 16);
+    int V;
+    pick_lanes(g, L.cl, V);
     const int nxmax = min(2 * g.pw, g.W);
     L.otab = min(g.ph * g.pw, max(PL_MAXOUT, g.pw));
     size_t smem;
     for (;;) {
-        L.zcap = max(2 * nxmax, (40 * 1024) / (L.cl * 16));
-        // plane byte offsets are packed into 16 bits
-        while ((size_t)L.zcap * L.cl * 16 > 65535 && L.zcap > 2 * nxmax) --L.zcap;
+        const size_t eb = (size_t)L.cl * V * 16;
+        L.zcap = (int)max((size_t)2 * nxmax, (size_t)((V == 1 ? 46 : 62) * 1024) / eb);   // 4 (V=1) / 3 (V=2) CTAs per SM
+        while ((size_t)L.zcap * eb > 65535 && L.zcap > 2 * nxmax) --L.zcap;     // plane offsets are packed in 16 bits
         smem = a16(sizeof(PlaneShared)) + sizeof(OutEntry) * (size_t)L.otab + a16(sizeof(unsigned) * (size_t)L.zcap) +
-               (size_t)L.zcap * L.cl * 16;
-        if (((size_t)L.zcap * L.cl * 16 <= 65535 && smem <= 200 * 1024) || L.cl == 1) break;
-        L.cl /= 2;
+               (size_t)L.zcap * eb;
+        if ((size_t)L.zcap * eb <= 65535 && smem <= 200 * 1024) break;
+        if (V > 1) V = 1; else if (L.cl > 1) L.cl /= 2; else return ROI3D_EUNSUPPORTED;
     }
-    if ((size_t)L.zcap * L.cl * 16 > 65535 || smem > 200 * 1024) return ROI3D_EUNSUPPORTED;
-    L.chunks = (g.C / 4 + L.cl - 1) / L.cl;
+    L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
+    auto kern = (V == 2) ? car3d_fwd_plane_kernel<2> : car3d_fwd_plane_kernel<1>;
     if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(car3d_fwd_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    car3d_fwd_plane_kernel<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops);
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
@@ -445,26 +531,27 @@ int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const 
                                   float *grad_image, cudaStream_t stream)
 {
     PlaneLaunch L;
-    L.cl = pick_cl(g, 16);
+    int V;
+    pick_lanes(g, L.cl, V);
     L.otab = 0;
-    const size_t fixed = a16(sizeof(PlaneShared)) + 2 * a16(sizeof(BwdRanges));
+    const size_t fixed = a16(sizeof(PlaneShared)) + a16(sizeof(BwdLists));
     size_t smem;
     for (;;) {
+        const size_t eb = (size_t)L.cl * V * 16;
         // stage whole k-slices when they fit ~50 KB, else tile over y samples
-        const int want = min(g.ph * g.pw, max(g.pw, (50 * 1024) / (L.cl * 16)));
-        L.zcap = max(want, g.pw);
-        smem = fixed + (size_t)L.zcap * L.cl * 16;
-        if (smem <= 200 * 1024 || L.cl == 1) break;
-        L.cl /= 2;
+        L.zcap = max(g.pw, min(g.ph * g.pw, (int)(((V == 1 ? 50 : 64) * 1024) / eb)));
+        smem = fixed + (size_t)L.zcap * eb;
+        if (smem <= 200 * 1024) break;
+        if (V > 1) V = 1; else if (L.cl > 1) L.cl /= 2; else return ROI3D_EUNSUPPORTED;
     }
-    if (smem > 200 * 1024) return ROI3D_EUNSUPPORTED;
-    L.chunks = (g.C / 4 + L.cl - 1) / L.cl;
+    L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
+    auto kern = (V == 2) ? car3d_grad_image_plane_kernel<2> : car3d_grad_image_plane_kernel<1>;
     if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(car3d_grad_image_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    car3d_grad_image_plane_kernel<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image);
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }

@@ -129,6 +129,8 @@ ROI3D_API int roi3d_car3d_grad_boxes(const float *grads, const float *image,
  * select a kernel variant; the defaults are the production choice.
  *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable
  *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
+ *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane kernels
+ *   "nms_variant"       reserved
  * Returns ROI3D_EINVAL for an unknown name.  roi3d_kernel_launches() returns
  * the number of kernel launches this library has enqueued on the calling
  * thread since the last roi3d_reset_kernel_launches().
