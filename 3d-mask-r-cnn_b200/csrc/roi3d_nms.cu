@@ -20,9 +20,11 @@
 //      mask[i][w] bit b = IoU(sorted i, sorted 32w+b) >= thr.  Row boxes staged in shared
 //      memory, one __ballot_sync per 32 pairs builds a mask word.  IoU is evaluated in the
 //      reference's fp32 operation order with IEEE division.
-//   3. nms_scan_kernel      : single-CTA greedy scan over 32-box chunks; warp 0 resolves a
-//      chunk serially from its diagonal word, all warps OR the kept rows into the
-//      shared-memory `removed` bitmap.  Emits original indices in selection order.
+//   3. nms_scan_kernel      : single-CTA warp-level greedy scan.  Warp 0 resolves 32-box chunks
+//      with ballot rounds out of a shared-memory copy of the diagonal mask block that the
+//      other warps prefetch one super-chunk ahead; all warps OR the kept rows into the
+//      shared-memory `removed` bitmap at super-chunk boundaries.  Emits original indices in
+//      selection order.
 #include "roi3d_common.cuh"
 #include <float.h>
 
@@ -46,7 +48,7 @@ __device__ __forceinline__ unsigned score_key(float s) {
 // ---------------------------------------------------------------------------------
 // 1. rank sort + gather
 // ---------------------------------------------------------------------------------
-constexpr int RS_ITILE = 32;        // boxes ranked per CTA
+constexpr int RS_ITILE = 8;         // boxes ranked per CTA
 constexpr int RS_JSPLIT = 32;       // threads sharing one box's j-range
 constexpr int RS_THREADS = RS_ITILE * RS_JSPLIT;
 constexpr int RS_KTILE = 4096;      // keys staged per shared-memory tile
@@ -65,6 +67,10 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
     if (threadIdx.x < RS_ITILE) s_rank[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_valid = 0;
     int cnt = 0, nvalid = 0;
+    // region split at 4-key vector granularity: keys strictly before the CTA's boxes precede on
+    // `key <= ki`, keys strictly after on `key < ki`; only the few vectors that straddle the CTA's
+    // own boxes need the full (key, index) comparison.  Padding keys are 0xFFFFFFFF with j >= n.
+    const int i_lo = (blockIdx.x * RS_ITILE) & ~3, i_hi = (blockIdx.x * RS_ITILE + RS_ITILE + 3) & ~3;
     for (int j0 = 0; j0 < n; j0 += RS_KTILE) {
         __syncthreads();
         const int tile = min(RS_KTILE, n - j0);
@@ -74,14 +80,24 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
             if (blockIdx.x == 0 && t < tile && k != 0xFFFFFFFFu) ++nvalid;
         }
         __syncthreads();
+        const int tile4 = (tile + 3) & ~3;
         // a box j precedes i iff key_j < key_i, or key_j == key_i and j < i
-        for (int t = jq * 4; t < tile; t += RS_JSPLIT * 4) {
+        const int t_lo = min(max(i_lo - j0, 0), tile4), t_hi = min(max(i_hi - j0, 0), tile4);
+        for (int t = jq * 4; t < t_lo; t += RS_JSPLIT * 4) {
+            const uint4 k4 = *reinterpret_cast<const uint4 *>(&s_keys[t]);
+            cnt += (k4.x <= ki) + (k4.y <= ki) + (k4.z <= ki) + (k4.w <= ki);
+        }
+        for (int t = t_lo + jq * 4; t < t_hi; t += RS_JSPLIT * 4) {
             const uint4 k4 = *reinterpret_cast<const uint4 *>(&s_keys[t]);
             const int j = j0 + t;
             cnt += (k4.x < ki) || (k4.x == ki && j + 0 < i);
-            cnt += (t + 1 < tile) && ((k4.y < ki) || (k4.y == ki && j + 1 < i));
-            cnt += (t + 2 < tile) && ((k4.z < ki) || (k4.z == ki && j + 2 < i));
-            cnt += (t + 3 < tile) && ((k4.w < ki) || (k4.w == ki && j + 3 < i));
+            cnt += (k4.y < ki) || (k4.y == ki && j + 1 < i);
+            cnt += (k4.z < ki) || (k4.z == ki && j + 2 < i);
+            cnt += (k4.w < ki) || (k4.w == ki && j + 3 < i);
+        }
+        for (int t = t_hi + jq * 4; t < tile4; t += RS_JSPLIT * 4) {
+            const uint4 k4 = *reinterpret_cast<const uint4 *>(&s_keys[t]);
+            cnt += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
         }
     }
     // reduce the RS_JSPLIT partial counts of each box (RS_JSPLIT == warp size)
@@ -118,19 +134,21 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
 // ---------------------------------------------------------------------------------
 // 2. pairwise IoU bitmask
 // ---------------------------------------------------------------------------------
-constexpr int MK_ROWS = 64;         // row boxes staged per CTA
+constexpr int MK_ROWS = 128;        // row boxes staged per CTA
 constexpr int MK_WARPS = 8;         // mask words (32 columns each) per CTA
 
-// IOU<float> (NMS.so@0xb500) on canonical boxes: same operations, same order.
-__device__ __forceinline__ bool iou_ge(const SBox &a, const float4 b0, const float4 b1, float thr) {
-    // b0 = (ymin,xmin,zmin,ymax)  b1 = (xmax,zmax,vol,-)
-    if (a.vol <= 0.0f || b1.z <= 0.0f) return 0.0f >= thr;
-    const float dy = fmaxf(0.0f, __fsub_rn(fminf(a.ymax, b0.w), fmaxf(a.ymin, b0.x)));
-    const float dx = fmaxf(0.0f, __fsub_rn(fminf(a.xmax, b1.x), fmaxf(a.xmin, b0.y)));
-    const float dz = fmaxf(0.0f, __fsub_rn(fminf(a.zmax, b1.y), fmaxf(a.zmin, b0.z)));
+// IOU<float> (NMS.so@0xb500) on canonical boxes: same operations, same order.  The reference's
+// early returns (volume <= 0 -> 0) need no test here: a box with a zero side has a zero
+// intersection with everything (dy <= side), and 0 / positive == 0 exactly.
+__device__ __forceinline__ bool iou_ge(const float4 a0, const float4 a1, const float4 b0, const float4 b1, float thr) {
+    // x0 = (ymin,xmin,zmin,ymax)  x1 = (xmax,zmax,vol,-)
+    const float dy = fmaxf(0.0f, __fsub_rn(fminf(a0.w, b0.w), fmaxf(a0.x, b0.x)));
+    const float dx = fmaxf(0.0f, __fsub_rn(fminf(a1.x, b1.x), fmaxf(a0.y, b0.y)));
+    const float dz = fmaxf(0.0f, __fsub_rn(fminf(a1.y, b1.y), fmaxf(a0.z, b0.z)));
     const float inter = __fmul_rn(__fmul_rn(dy, dx), dz);
-    if (!(inter > 0.0f)) return 0.0f >= thr;                  // 0 / positive == 0 exactly
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.vol, b1.z), inter));
+    if (!(inter > 0.0f)) return 0.0f >= thr;
+    if (a1.z <= 0.0f || b1.z <= 0.0f) return 0.0f >= thr;     // volume product underflowed to 0 (reference returns 0)
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a1.z, b1.z), inter));
     return iou >= thr;
 }
 
@@ -138,114 +156,204 @@ __global__ void __launch_bounds__(MK_WARPS * 32)
 nms_mask_kernel(const SBox *__restrict__ sboxes, int n, int pitch_words, float thr,
                 unsigned *__restrict__ mask)
 {
-    __shared__ SBox s_rows[MK_ROWS];
+    __shared__ float4 s_rows[MK_ROWS * 2];
     const int i0 = blockIdx.y * MK_ROWS;
     const int w0 = blockIdx.x * MK_WARPS;
-    // only words that contain some column j > i0 are ever read by the scan
+    // only words that contain some column j >= i0 are ever read by the scan
     if ((w0 + MK_WARPS) * 32 <= i0) return;
     const int rows = min(MK_ROWS, n - i0);
     for (int t = threadIdx.x; t < rows * 2; t += blockDim.x)
-        reinterpret_cast<float4 *>(s_rows)[t] = __ldg(reinterpret_cast<const float4 *>(sboxes + i0) + t);
+        s_rows[t] = __ldg(reinterpret_cast<const float4 *>(sboxes + i0) + t);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = w0 + warp;
     if (w * 32 >= n || (w + 1) * 32 <= i0) return;
     const int j = w * 32 + lane;
-    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // padding columns (j >= n): a far-away zero-size box never intersects anything
+    float4 b0 = make_float4(3e38f, 3e38f, 3e38f, 3e38f), b1 = make_float4(3e38f, 3e38f, 0.f, 0.f);
     if (j < n) {
         b0 = __ldg(reinterpret_cast<const float4 *>(sboxes + j));
         b1 = __ldg(reinterpret_cast<const float4 *>(sboxes + j) + 1);
     }
-    unsigned word0 = 0, word1 = 0;
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
-        const bool bit = (j < n) && iou_ge(s_rows[r], b0, b1, thr);
-        const unsigned wd = __ballot_sync(0xffffffffu, bit);
-        if (r < 32) { if (lane == r) word0 = wd; }
-        else        { if (lane == r - 32) word1 = wd; }
+    const bool pad_bit = (j >= n);
+    for (int rb = 0; rb < rows; rb += 32) {
+        // rows whose word lies entirely below the diagonal are never read
+        if ((w + 1) * 32 <= i0 + rb) continue;
+        unsigned word = 0;
+        const int rend = min(32, rows - rb);
+#pragma unroll 8
+        for (int r = 0; r < rend; ++r) {
+            const bool bit = iou_ge(s_rows[2 * (rb + r)], s_rows[2 * (rb + r) + 1], b0, b1, thr) && !pad_bit;
+            const unsigned wd = __ballot_sync(0xffffffffu, bit);
+            if (lane == r) word = wd;
+        }
+        if (lane < rend) mask[(size_t)(i0 + rb + lane) * pitch_words + w] = word;
     }
-    if (lane < rows) mask[(size_t)(i0 + lane) * pitch_words + w] = word0;
-    if (lane + 32 < rows) mask[(size_t)(i0 + 32 + lane) * pitch_words + w] = word1;
 }
 
 // ---------------------------------------------------------------------------------
-// 3. greedy scan (single CTA)
+// 3. greedy scan (single CTA, warp-level)
+//
+// Boxes are visited in super-chunks of SC_SB = 512 sorted boxes (16 mask words).  While warp 0
+// resolves super-chunk s, the other warps prefetch the 512 x 16-word diagonal block of
+// super-chunk s+1 into shared memory, so the serial chain of warp 0 touches only shared
+// memory and registers:
+//   - lane w (< 16) keeps word w of the super-chunk's `removed` bits in a register;
+//   - a 32-box chunk is resolved with the parallel greedy rule (a box is kept once every
+//     earlier conflicting box of the chunk is decided removed; it is removed once one of them
+//     is decided kept) -- a few __ballot_sync rounds instead of 32 dependent steps;
+//   - the kept rows of the chunk are OR-ed into the lanes' words from the shared block.
+// At a super-chunk boundary all 32 warps OR the kept rows (global mask, coalesced row reads)
+// into the shared `removed` bitmap of the not-yet-visited words.
 // ---------------------------------------------------------------------------------
 constexpr int SC_THREADS = 1024;
+constexpr int SC_SB = 512;                 // boxes per super-chunk
+constexpr int SC_W = SC_SB / 32;           // words per super-chunk row (16)
+constexpr int SC_P = SC_W + 1;             // padded row pitch in shared memory (bank-conflict free diagonal reads)
+
+// stage super-chunk s: its 512 x 16-word diagonal mask block, the boxes' volumes and original indices
+__device__ __forceinline__ void sc_prefetch(unsigned *dst, float *vol, int *sidx, const unsigned *__restrict__ mask,
+                                            int pitch_words, const SBox *__restrict__ sboxes,
+                                            const int *__restrict__ sorted_idx, int s, int nvalid, int nwords,
+                                            int tid0, int nthreads)
+{
+    const int row0 = s * SC_SB, w0 = s * SC_W;
+    for (int t = tid0; t < SC_SB * SC_W; t += nthreads) {
+        const int r = t / SC_W, w = t % SC_W;
+        unsigned v = 0u;
+        if (row0 + r < nvalid && w0 + w < nwords) v = __ldg(mask + (size_t)(row0 + r) * pitch_words + w0 + w);
+        dst[r * SC_P + w] = v;
+    }
+    for (int r = tid0; r < SC_SB; r += nthreads) {
+        const bool ok = row0 + r < nvalid;
+        vol[r] = ok ? sboxes[row0 + r].vol : 1.0f;
+        sidx[r] = ok ? __ldg(sorted_idx + row0 + r) : -1;
+    }
+}
 
 __global__ void __launch_bounds__(SC_THREADS)
 nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *__restrict__ sboxes,
                 const int *__restrict__ sorted_idx, const int *__restrict__ nvalid_p,
                 int max_out, float thr, int *__restrict__ keep_idx, int *__restrict__ keep_count)
 {
-    extern __shared__ unsigned s_removed[];                    // pitch_words words
-    __shared__ unsigned s_kept;
-    __shared__ int s_nsel;
-    __shared__ int s_fill;                                     // >= 0: zero-volume quirk, repeat this index
+    extern __shared__ unsigned s_dyn[];
+    unsigned *s_removed = s_dyn;                               // pitch_words words
+    unsigned *s_blk = s_dyn + pitch_words;                     // 2 x SC_SB x SC_P words
+    float *s_vol = reinterpret_cast<float *>(s_blk + 2 * SC_SB * SC_P);   // 2 x SC_SB
+    int *s_sidx = reinterpret_cast<int *>(s_vol + 2 * SC_SB);             // 2 x SC_SB
+    __shared__ int s_krows[SC_SB];                             // kept rows of the current super-chunk
+    __shared__ int s_nk, s_nsel, s_fill, s_done;
     const int nvalid = *nvalid_p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int nwords = (nvalid + 31) >> 5;
+    const int nsuper = (nvalid + SC_SB - 1) / SC_SB;
     for (int t = threadIdx.x; t < pitch_words; t += blockDim.x) s_removed[t] = 0u;
-    if (threadIdx.x == 0) { s_nsel = 0; s_fill = -1; s_kept = 0u; }
-    const int nchunks = (nvalid + 31) >> 5;
-    int nsel = 0;
-    for (int c = 0; c < nchunks && nsel < max_out; ++c) {
-        __syncthreads();                                       // removed[c] final, s_nsel visible
-        if (warp == 0) {
-            unsigned rw = s_removed[c];
-            const int row = c * 32 + lane;
-            unsigned d = 0u;
-            bool degenerate = false;
-            if (row < nvalid) {
-                d = __ldg(mask + (size_t)row * pitch_words + c);
-                degenerate = !(sboxes[row].vol > 0.0f) && !(0.0f >= thr);   // self-IoU 0 < thr
-            } else {
-                rw |= (1u << lane);
+    if (threadIdx.x == 0) { s_nsel = 0; s_fill = -1; s_done = 0; s_nk = 0; }
+    sc_prefetch(s_blk, s_vol, s_sidx, mask, pitch_words, sboxes, sorted_idx, 0, nvalid, nwords, threadIdx.x, SC_THREADS);
+    __syncthreads();
+    const bool self_suppresses = (0.0f >= thr);                // thr == 0: even a zero-volume box suppresses itself
+
+    for (int s = 0; s < nsuper; ++s) {
+        unsigned *blk = s_blk + (s & 1) * (SC_SB * SC_P);
+        const float *bvol = s_vol + (s & 1) * SC_SB;
+        const int *bsidx = s_sidx + (s & 1) * SC_SB;
+        if (warp != 0) {
+            // background: stage the diagonal block of the next super-chunk
+            if (s + 1 < nsuper) {
+                const int nb = (s + 1) & 1;
+                sc_prefetch(s_blk + nb * (SC_SB * SC_P), s_vol + nb * SC_SB, s_sidx + nb * SC_SB, mask, pitch_words,
+                            sboxes, sorted_idx, s + 1, nvalid, nwords, threadIdx.x - 32, SC_THREADS - 32);
             }
-            rw = __reduce_or_sync(0xffffffffu, rw);
-            const unsigned degen = __ballot_sync(0xffffffffu, degenerate);
-            unsigned kept = 0u;
-            int fill_row = -1, nk = 0;
-            for (int b = 0; b < 32; ++b) {
-                const unsigned db = __shfl_sync(0xffffffffu, d, b);
-                if (!((rw >> b) & 1u)) {
-                    kept |= (1u << b);
-                    rw |= db;
-                    ++nk;
-                    if ((degen >> b) & 1u) { fill_row = c * 32 + b; break; }
-                    if (nsel + nk >= max_out) break;
+        } else {
+            int nsel = s_nsel, nk = 0, fill = -1;
+            bool done = false;
+            unsigned rem = (lane < SC_W && s * SC_W + lane < nwords) ? s_removed[s * SC_W + lane] : 0xFFFFFFFFu;
+            const unsigned lt = (1u << lane) - 1u;
+            for (int c = 0; c < SC_W && !done; ++c) {
+                const int row = s * SC_SB + c * 32 + lane;
+                if (s * SC_SB + c * 32 >= nvalid) break;
+                const unsigned rw = __shfl_sync(0xffffffffu, rem, c);
+                const bool valid = row < nvalid;
+                const unsigned d = valid ? blk[(c * 32 + lane) * SC_P + c] : 0u;
+                const unsigned sup = d & lt;                   // earlier boxes of this chunk that conflict with me
+                unsigned undecided = __ballot_sync(0xffffffffu, valid && !((rw >> lane) & 1u));
+                unsigned kept = 0u;
+                while (undecided) {
+                    const bool me = (undecided >> lane) & 1u;
+                    const bool drop = me && (sup & kept);
+                    const bool keep = me && !drop && !(sup & undecided);
+                    const unsigned nkp = __ballot_sync(0xffffffffu, keep);
+                    const unsigned ndr = __ballot_sync(0xffffffffu, drop);
+                    kept |= nkp;
+                    undecided &= ~(nkp | ndr);
+                }
+                // zero-volume quirk (NMS.so@0xdc55): a selected box whose self-IoU is 0 is selected again
+                // until max_out; everything after it is never reached
+                const bool degenerate = valid && !(bvol[c * 32 + lane] > 0.0f) && !self_suppresses;
+                const unsigned degen = __ballot_sync(0xffffffffu, degenerate) & kept;
+                if (degen) {
+                    const int bq = __ffs(degen) - 1;
+                    kept &= (2u << bq) - 1u;
+                    fill = s * SC_SB + c * 32 + bq;
+                    done = true;
+                }
+                int cnt = __popc(kept);
+                if (nsel + cnt >= max_out) {                   // keep only the first (max_out - nsel) of them
+                    const int room = max_out - nsel;
+                    if (cnt > room) {
+                        const bool mine = ((kept >> lane) & 1u) && __popc(kept & lt) < room;
+                        kept = __ballot_sync(0xffffffffu, mine);
+                        cnt = room;
+                        fill = -1;                             // the degenerate box (if any) was beyond max_out
+                    }
+                    done = true;
+                }
+                if ((kept >> lane) & 1u) {
+                    const int slot = __popc(kept & lt);
+                    keep_idx[nsel + slot] = bsidx[c * 32 + lane];
+                    s_krows[nk + slot] = row;
+                }
+                nsel += cnt;
+                nk += cnt;
+                // OR the kept rows into the super-chunk's removed words: lane b offers row b of the block,
+                // one warp OR-reduction per remaining word, lane w keeps word w
+                {
+                    const bool mine = (kept >> lane) & 1u;
+                    const unsigned *myrow = blk + (c * 32 + lane) * SC_P;
+#pragma unroll
+                    for (int w = 1; w < SC_W; ++w) {
+                        if (w > c) {
+                            const unsigned v = __reduce_or_sync(0xffffffffu, mine ? myrow[w] : 0u);
+                            if (lane == w) rem |= v;
+                        }
+                    }
                 }
             }
-            if ((kept >> lane) & 1u)
-                keep_idx[nsel + __popc(kept & ((1u << lane) - 1u))] = __ldg(sorted_idx + row);
             if (lane == 0) {
-                s_kept = kept;
-                s_nsel = nsel + nk;
-                s_fill = (fill_row >= 0) ? __ldg(sorted_idx + fill_row) : -1;
+                s_nsel = nsel;
+                s_nk = nk;
+                s_done = done || nsel >= max_out;
+                s_fill = (fill >= 0) ? bsidx[fill - s * SC_SB] : -1;
             }
         }
         __syncthreads();
-        const unsigned kept = s_kept;
-        nsel = s_nsel;
-        if (s_fill >= 0) break;
-        // OR the kept rows into removed[w] for w > c (one warp per kept row)
-        unsigned kk = kept;
-        int q = 0;
-        while (kk) {
-            const int b = __ffs(kk) - 1;
-            kk &= kk - 1;
-            if ((q++ % nwarps) == warp) {
-                const unsigned *mrow = mask + (size_t)(c * 32 + b) * pitch_words;
-                for (int w = c + 1 + lane; w < nchunks; w += 32) {
+        if (s_done) break;
+        // boundary: every warp ORs kept rows into the not-yet-visited words
+        const int nk = s_nk, wfirst = (s + 1) * SC_W;
+        if (wfirst < nwords) {
+            for (int q = warp; q < nk; q += SC_THREADS / 32) {
+                const unsigned *mrow = mask + (size_t)s_krows[q] * pitch_words;
+                for (int w = wfirst + lane; w < nwords; w += 32) {
                     const unsigned m = __ldg(mrow + w);
                     if (m) atomicOr(&s_removed[w], m);
                 }
             }
         }
+        __syncthreads();
     }
     __syncthreads();
+    int nsel = s_nsel;
     const int fill = s_fill;
-    nsel = s_nsel;
     if (fill >= 0) {                                           // zero-volume quirk: repeat until max_out
         for (int t = nsel + threadIdx.x; t < max_out; t += blockDim.x) keep_idx[t] = fill;
         nsel = max_out;
@@ -287,7 +395,7 @@ int launch_nms3d(const float *boxes, const float *scores, int n, int max_out, fl
     }
     const NmsLayout L = nms_layout(n);
     if (ws == nullptr || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return ROI3D_EWORKSPACE;
-    if ((size_t)L.pitch_words * sizeof(unsigned) > 200 * 1024) return ROI3D_EUNSUPPORTED;   // > 1.6 M boxes
+    if ((size_t)L.pitch_words * sizeof(unsigned) > 128 * 1024) return ROI3D_EUNSUPPORTED;   // > 1 M boxes
     char *base = static_cast<char *>(ws);
     int *nvalid = reinterpret_cast<int *>(base + L.off_nvalid);
     int *sidx = reinterpret_cast<int *>(base + L.off_sidx);
@@ -300,9 +408,8 @@ int launch_nms3d(const float *boxes, const float *scores, int n, int max_out, fl
     dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS);
     nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, n, L.pitch_words, thr, mask);
     ROI3D_LAUNCH_CHECK();
-    const size_t smem = (size_t)L.pitch_words * sizeof(unsigned);
-    if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = ((size_t)L.pitch_words + 2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
+    ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_scan_kernel<<<1, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, max_out, thr,
                                                     keep_idx, keep_count);
     ROI3D_LAUNCH_CHECK();
