@@ -31,6 +31,17 @@ __device__ __forceinline__ Sample make_sample(float a1, float a2, int dim, int p
     return s;
 }
 
+__device__ __forceinline__ Sample make_sample_scaled(float a1, float a2, int dim, int p, int k, float scale) {
+    Sample s;
+    s.in = axis_coord(a1, a2, dim, p, k, scale);
+    s.valid = !axis_invalid(s.in, dim);
+    const float fl = floorf(s.in);
+    s.i0 = (int)fl;
+    s.i1 = (int)ceilf(s.in);
+    s.t = __fsub_rn(s.in, fl);
+    return s;
+}
+
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
 template <> struct VecT<1> { using type = float; };
@@ -169,6 +180,12 @@ car3d_grad_boxes_kernel(const float *__restrict__ grads, const float *__restrict
     const float rh = (g.ph > 1) ? __fdiv_rn((float)(g.H - 1), (float)(g.ph - 1)) : 0.0f;
     const float rw = (g.pw > 1) ? __fdiv_rn((float)(g.W - 1), (float)(g.pw - 1)) : 0.0f;
     const float rd = (g.pd > 1) ? __fdiv_rn((float)(g.D - 1), (float)(g.pd - 1)) : 0.0f;
+    // This op forms the sample step as (a2 - a1) * ratio (GB.so@0x3ff6-0x4071), not as the forward's
+    // ((a2 - a1) * (dim - 1)) / (p - 1).  REFERENCE QUIRK reproduced for parity: its depth step is
+    // (z2 - y1) * ratio_h (GB.so@0x4059-0x4071 loads box[5], box[0] and the height ratio).
+    const float hs = (g.ph > 1) ? __fmul_rn(__fsub_rn(y2, y1), rh) : 0.0f;
+    const float ws = (g.pw > 1) ? __fmul_rn(__fsub_rn(x2, x1), rw) : 0.0f;
+    const float ds = (g.pd > 1) ? __fmul_rn(__fsub_rn(z2, y1), rh) : 0.0f;
     const float *img = image + (long long)__ldg(box_ind + b) * g.H * sH;
     const float *gb = grads + (long long)b * g.ph * g.pw * g.pd * g.C;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -179,9 +196,9 @@ car3d_grad_boxes_kernel(const float *__restrict__ grads, const float *__restrict
         const int z = (int)(r % g.pd); r /= g.pd;
         const int x = (int)(r % g.pw);
         const int y = (int)(r / g.pw);
-        const Sample sy = make_sample(y1, y2, g.H, g.ph, y);
-        const Sample sx = make_sample(x1, x2, g.W, g.pw, x);
-        const Sample sz = make_sample(z1, z2, g.D, g.pd, z);
+        const Sample sy = make_sample_scaled(y1, y2, g.H, g.ph, y, hs);
+        const Sample sx = make_sample_scaled(x1, x2, g.W, g.pw, x, ws);
+        const Sample sz = make_sample_scaled(z1, z2, g.D, g.pd, z, ds);
         if (!(sy.valid && sx.valid && sz.valid)) continue;
         const float *pt = img + sy.i0 * sH + c, *pb = img + sy.i1 * sH + c;
         const long long ol = sx.i0 * sW, orr = sx.i1 * sW, of = sz.i0 * sD, oc = sz.i1 * sD;

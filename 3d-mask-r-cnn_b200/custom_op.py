@@ -80,7 +80,7 @@ class _Arg:
             if t.dtype != dtype:
                 t = t.to(dtype)
             t = t.contiguous()
-            if not t.is_pinned() and t.numel() * t.element_size() >= (1 << 16):
+            if not t.is_pinned() and t.numel() * t.element_size() >= (1 << 20):
                 t = t.pin_memory()                     # pageable -> pinned staging, then one async H2D
             self.dev = t.to(device, non_blocking=True)
         else:

@@ -39,6 +39,8 @@ ROIS_PER_IMAGE = 128
 CROPS = ((7, 7, 7), (14, 14, 14))
 METRIC = "3D ROIAlign fwd+bwd ROIs/s"
 UNIT = "ROIs/s"
+WORKLOAD = ("cfg2: batch 2 x 128^3, 128 ROIs/image, P2-P5 C=256, CropAndResize3D fwd + grad-image "
+            "for 7^3 and 14^3 heads (16 op calls/step)")
 
 
 def load_peaks():
@@ -85,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -172,12 +174,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    rb.reset_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        # the sampler runs from the warm-up (same kernels, same load) through the timed region so that a
+        # millisecond-scale region still yields several nvidia-smi samples under load
+        t_w = time.perf_counter()
+        nw = 0
+        while nw < max(args.warmup, 3) or time.perf_counter() - t_w < 0.6:
+            step()
+            nw += 1
+            if nw % 50 == 0:
+                torch.cuda.synchronize()
+        barrier()
+        rb.reset_kernel_launches()
         barrier()
         e0.record()
         for _ in range(args.steps):
@@ -284,8 +293,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: batch 2 x 128^3, 128 ROIs/image, P2-P5 C=256, CropAndResize3D fwd + grad-image "
-                               "for 7^3 and 14^3 heads (16 op calls/step)",
+        "config": {"workload": WORKLOAD,
                    "rois_per_step_per_gpu": total_rois, "l2": "inputs larger than L2 (feature maps 356 MB + grads "
                    "809 MB per step; no explicit flush)", "sharding": "one batch per GPU, no collective"},
         "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
@@ -298,8 +306,15 @@ def run_ours(args):
         "ops": per_op,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(ops, threads=None)
-        line["cpu_baseline_1thread"] = cpu_baseline(ops, threads=1, sample_rois=32)
+        _, ref = _cpu_engines()
+        nthr = host_threads()
+        if ref is not None:
+            line["cpu_baseline"] = cpu_baseline(ops, "reference", min(nthr, 16), 64)
+            line["cpu_baseline_reference_1thread"] = cpu_baseline(ops, "reference", 1, 32)
+            line["cpu_baseline_port_allcores"] = cpu_baseline(ops, "port", nthr, 64)
+        else:
+            line["cpu_baseline"] = cpu_baseline(ops, "port", nthr, 64)
+            line["cpu_baseline_port_1thread"] = cpu_baseline(ops, "port", 1, 32)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -307,76 +322,111 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU baseline = the oracle port of the reference kernels (test infrastructure, never the product)
+# CPU baselines (test infrastructure, never the product):
+#   kind "reference": the reference's OWN compiled kernels (oracle/_ref, run by oracle/refrun without
+#                     TensorFlow).  They are single-threaded; the independent op nodes of a step run
+#                     concurrently on a thread pool, which is all the parallelism TF's inter-op pool
+#                     could give them.
+#   kind "port":      the C oracle (bit-identical to the above) with OpenMP over boxes / channels on all
+#                     host cores -- a generous upper bound for a CPU implementation of the same algorithm.
 # ------------------------------------------------------------------------------------------
-def cpu_step(ops, threads, sample_rois):
-    """One step on the host over the first `sample_rois` ROIs of every op; returns (seconds, rois, fill_s)."""
+def _cpu_engines():
     import oracle
-    t_all, t_fill, done = 0.0, 0.0, 0
+    try:
+        from oracle import refrun
+        ref = refrun.load()
+    except Exception:  # noqa: BLE001
+        ref = None
+    return oracle, ref
+
+
+def cpu_step(ops, kind, threads, sample_rois):
+    """One step on the host over the first `sample_rois` ROIs (spread over the ops like the full step).
+    Returns (seconds for the sampled step, ROIs done, seconds of the zero-fill-only part)."""
+    from concurrent.futures import ThreadPoolExecutor
+    oracle, ref = _cpu_engines()
     frac = min(1.0, sample_rois / float(BATCH * ROIS_PER_IMAGE))
+    sub = []
+    done = 0
     for op in ops:
-        n = int(round(op["n"] * frac)) if op["n"] else 0
-        n = max(n, 1) if op["n"] else 0
-        bx, bi, g = op["boxes"][:n], op["bidx"][:n], op["grads"][:n]
-        t0 = time.perf_counter()
-        oracle.crop_and_resize_3d(op["image"], bx, bi, op["crop"], threads=threads)
-        t1 = time.perf_counter()
-        oracle.crop_and_resize_3d_grad_image(g, bx, bi, op["shape"], threads=threads)
-        t2 = time.perf_counter()
-        oracle.crop_and_resize_3d_grad_image(g[:0], bx[:0], bi[:0], op["shape"], threads=threads)   # zero-fill only
-        t3 = time.perf_counter()
-        t_all += t2 - t0
-        t_fill += t3 - t2
+        n = max(int(round(op["n"] * frac)), 1) if op["n"] else 0
+        sub.append((op, op["boxes"][:n], op["bidx"][:n], op["grads"][:n]))
         if op["crop"] == CROPS[0]:
             done += n
-    return t_all, done, t_fill
+    if kind == "reference":
+        fwd = [lambda o=o, b=b, i=i: ref.crop_and_resize_3d(o["image"], b, i, o["crop"]) for o, b, i, g in sub if len(b)]
+        bwd = [lambda o=o, b=b, i=i, g=g: ref.crop_and_resize_3d_grad_image(g, b, i, o["shape"]) for o, b, i, g in sub]
+        fill = [lambda o=o, b=b, i=i, g=g: ref.crop_and_resize_3d_grad_image(g[:0], b[:0], i[:0], o["shape"]) for o, b, i, g in sub]
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            t0 = time.perf_counter()
+            list(ex.map(lambda f: f(), fwd))
+            list(ex.map(lambda f: f(), bwd))
+            t1 = time.perf_counter()
+            list(ex.map(lambda f: f(), fill))
+            t2 = time.perf_counter()
+    else:
+        t0 = time.perf_counter()
+        for o, b, i, g in sub:
+            if len(b):
+                oracle.crop_and_resize_3d(o["image"], b, i, o["crop"], threads=threads)
+        for o, b, i, g in sub:
+            oracle.crop_and_resize_3d_grad_image(g, b, i, o["shape"], threads=threads)
+        t1 = time.perf_counter()
+        for o, b, i, g in sub:
+            oracle.crop_and_resize_3d_grad_image(g[:0], b[:0], i[:0], o["shape"], threads=threads)
+        t2 = time.perf_counter()
+    return t1 - t0, done, t2 - t1
 
 
-def cpu_baseline(ops, threads=None, sample_rois=64):
-    import oracle
-    threads = threads or oracle.max_threads()
+def cpu_baseline(ops, kind, threads, sample_rois):
     total = BATCH * ROIS_PER_IMAGE
-    t_all, done, t_fill = cpu_step(ops, threads, sample_rois)
-    # per-ROI work scales with the ROI count, the zero-fill of the 8 grad images is paid once per step
-    t_step = t_fill + (t_all - t_fill) * total / max(done, 1)
-    return {"value": round(total / t_step, 3), "unit": UNIT, "cores": threads, "kind": "port",
+    t_all, done, t_fill = cpu_step(ops, kind, threads, sample_rois)
+    # per-ROI work scales with the ROI count; the zero-fill of the 8 grad images is paid once per step
+    t_step = min(t_fill, t_all) + max(t_all - t_fill, 0.0) * total / max(done, 1)
+    how = ("the reference's own compiled kernels (oracle/_ref via oracle/refrun), op nodes of the step run "
+           "concurrently on %d threads" % threads) if kind == "reference" else \
+          ("C oracle port, OpenMP over boxes (fwd) / channels (bwd) on %d threads" % threads)
+    return {"value": round(total / t_step, 3), "unit": UNIT, "cores": threads, "kind": kind,
             "sample": "%d of %d ROIs through all 16 ops on full-size feature maps (%.1f s of CPU work); step time "
-                      "extrapolated as zero-fill + per-ROI time x 256" % (done, total, t_all),
+                      "= zero-fill + per-ROI time x %d; %s" % (done, total, t_all, total, how),
             "ms_per_step": round(t_step * 1e3, 1)}
 
 
+def host_threads():
+    import oracle
+    return max(1, oracle.max_threads())
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the step (oracle port of the wheel's kernels; the binaries
-    themselves need TF 2.2 / cp36 and cannot run), all host threads, same config/metric/unit."""
+    """The reference's CPU implementation of the step on the box's host cores: its own compiled kernels
+    (oracle/_ref) when available, else the bit-identical C port; same config / metric / unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
+    oracle, ref = _cpu_engines()
+    kind = "reference" if ref is not None else "port"
     ops = make_workload(seed=2002)
-    threads = oracle.max_threads()
+    threads = min(host_threads(), 16) if kind == "reference" else host_threads()
     total = BATCH * ROIS_PER_IMAGE
     sample = 64
     for _ in range(min(args.warmup, 1)):
-        cpu_step(ops, threads, 8)
-    t_sum, vals = 0.0, []
-    for _ in range(args.steps):
-        t_all, done, t_fill = cpu_step(ops, threads, sample)
-        t_step = t_fill + (t_all - t_fill) * total / max(done, 1)
-        vals.append(t_step)
-        t_sum += t_all
-        if t_sum > 150:
+        cpu_step(ops, kind, threads, 8)
+    t_sum, vals, last = 0.0, [], None
+    for _ in range(max(args.steps, 1)):
+        last = cpu_baseline(ops, kind, threads, sample)
+        vals.append(last["ms_per_step"] * 1e-3)
+        t_sum += vals[-1] * sample / total
+        if t_sum > 120:
             break
     t_step = statistics.mean(vals)
     value = round(total / t_step, 3)
+    last["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": min(args.warmup, 1), "ms_per_step": round(t_step * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: batch 2 x 128^3, 128 ROIs/image, P2-P5 C=256, CropAndResize3D fwd + grad-image "
-                               "for 7^3 and 14^3 heads (16 op calls/step)", "rois_per_step_per_gpu": total},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d of %d ROIs per step through all 16 ops, full-size feature maps; step time = "
-                                   "zero-fill + per-ROI time x 256; OpenMP over boxes (fwd) / channels (bwd)" % (sample, total)},
+        "config": {"workload": WORKLOAD, "rois_per_step_per_gpu": total},
+        "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

@@ -15,12 +15,16 @@
  * <lib>@0xADDR as in SURVEY.md section 0) and the Python call sites in
  * core/custom_op/custom_op.py:22-65 and core/models.py:450-456, 663-664.
  *
- * Parity pin.  (1) iou3d is checked bit-for-bit against the reference's own
- * IOU<float> machine code lifted from the wheel (tests/test_oracle_pin.py,
- * oracle/lift_iou.py).  (2) All four ops are checked bit-for-bit against the
- * reference's own Compute() functions executed in this container through the
- * stub TF runtime in oracle/refrun/ (when built; see oracle/README.md).  The
- * committed golden vectors under tests/golden/ were produced by those runs.
+ * Parity pin: PINNED.  oracle/refrun/ maps the wheel's four shared objects
+ * into this process (its own ELF loader + stand-ins for the ~25 TensorFlow
+ * call-outs) and runs the reference's OWN Compute() functions and its own
+ * IOU<float>.  tests/test_oracle_pin.py asserts that every function below is
+ * bit-identical to them (forward, grad-image, grad-boxes, NMS, 200k IoU
+ * pairs; edge cases included), and tests/golden/*.npz were written by
+ * `make_golden.py --check-ref`, i.e. only after the same check passed.
+ * Two reference defects found that way are documented where they apply:
+ * the grad-boxes depth step (restated faithfully) and the `nearest` forward
+ * loop bound (undefined behaviour upstream for crop_width != crop_depth).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile): every
  * fp32 operation below is a separately rounded IEEE op, like the reference's
@@ -229,7 +233,10 @@ static void car3d_fwd_box(const float *image, int H, int W, int D, int C,
                         const float bot = bl + (br - bl) * xl;
                         oz[c] = top + (bot - top) * yl;
                     }
-                } else {                          /* nearest @0x54c2-0x54e8 */
+                } else {                          /* nearest @0x54c2-0x54e8.  NB: the reference's nearest branch bounds its
+                                                   * z loop by crop_width (cmp [rbp-0xa4] @0x5570), so for pw != pd it leaves
+                                                   * crop voxels unwritten (pw < pd) or writes past the row (pw > pd):
+                                                   * undefined behaviour.  For pw == pd (every caller) it is this code. */
                     const int yi = (int)roundf(in_y), xi = (int)roundf(in_x), zi = (int)roundf(in_z);
                     const float *p = img + yi * sH + xi * sW + zi * sD;
                     for (int c = 0; c < C; ++c) oz[c] = p[c];
@@ -361,7 +368,7 @@ ORACLE_API void roi3d_oracle_car3d_grad_boxes(const float *grads, const float *i
 {
     (void)B;
     const size_t sD = (size_t)C, sW = (size_t)D * C, sH = (size_t)W * D * C;
-    const float rh = (ph > 1) ? (float)(H - 1) / (float)(ph - 1) : 0.0f;
+    const float rh = (ph > 1) ? (float)(H - 1) / (float)(ph - 1) : 0.0f;        /* @0x3f4a-0x3f65 */
     const float rw = (pw > 1) ? (float)(W - 1) / (float)(pw - 1) : 0.0f;
     const float rd = (pd > 1) ? (float)(D - 1) / (float)(pd - 1) : 0.0f;
     memset(out, 0, sizeof(float) * (size_t)n * 6);
@@ -369,9 +376,16 @@ ORACLE_API void roi3d_oracle_car3d_grad_boxes(const float *grads, const float *i
         const float *box = boxes + (size_t)b * 6;
         const float y1 = box[0], x1 = box[1], z1 = box[2];
         const float y2 = box[3], x2 = box[4], z2 = box[5];
-        const float hs = axis_scale(y1, y2, H, ph);
-        const float ws = axis_scale(x1, x2, W, pw);
-        const float ds = axis_scale(z1, z2, D, pd);
+        /* Unlike the forward and grad-image kernels, this op forms the sample step as
+         * (a2 - a1) * ratio (GB.so@0x3ff6-0x4071, the TF crop_and_resize_op.cc form).
+         * REFERENCE QUIRK, restated on purpose: the depth step is computed from the wrong
+         * operands, (z2 - y1) * ratio_h instead of (z2 - z1) * ratio_d (GB.so@0x4059-0x4071
+         * loads box[5], box[0] and the height ratio).  The op is never executed by
+         * core/models.py (boxes are stop_gradient'ed, core/models.py:660), so the slip went
+         * unnoticed upstream; parity means reproducing it. */
+        const float hs = (ph > 1) ? (y2 - y1) * rh : 0.0f;
+        const float ws = (pw > 1) ? (x2 - x1) * rw : 0.0f;
+        const float ds = (pd > 1) ? (z2 - y1) * rh : 0.0f;
         const float *img = image + (size_t)box_ind[b] * H * sH;
         float *o = out + (size_t)b * 6;
         for (int y = 0; y < ph; ++y) {
@@ -409,22 +423,25 @@ ORACLE_API void roi3d_oracle_car3d_grad_boxes(const float *grads, const float *i
                             o[0] += gy * ((float)(H - 1) - (float)y * rh);
                             o[3] += (gy * (float)y) * rh;
                         } else {
-                            const float v = (float)((double)gy * 0.5 * (double)(H - 1));
-                            o[0] += v; o[3] += v;
+                            /* accumulated in double, rounded once (GB.so@0x47d0-0x4829) */
+                            const double v = (double)gy * 0.5 * (double)(H - 1);
+                            o[0] = (float)((double)o[0] + v); o[3] = (float)(v + (double)o[3]);
                         }
                         if (pw > 1) {
                             o[1] += gx * ((float)(W - 1) - (float)x * rw);
                             o[4] += (gx * (float)x) * rw;
                         } else {
-                            const float v = (float)((double)gx * 0.5 * (double)(W - 1));
-                            o[1] += v; o[4] += v;
+                            /* accumulated in double, rounded once (GB.so@0x47d0-0x4829) */
+                            const double v = (double)gx * 0.5 * (double)(W - 1);
+                            o[1] = (float)((double)o[1] + v); o[4] = (float)(v + (double)o[4]);
                         }
                         if (pd > 1) {
                             o[2] += gz * ((float)(D - 1) - (float)z * rd);
                             o[5] += (gz * (float)z) * rd;
                         } else {
-                            const float v = (float)((double)gz * 0.5 * (double)(D - 1));
-                            o[2] += v; o[5] += v;
+                            /* accumulated in double, rounded once (GB.so@0x47d0-0x4829) */
+                            const double v = (double)gz * 0.5 * (double)(D - 1);
+                            o[2] = (float)((double)o[2] + v); o[5] = (float)(v + (double)o[5]);
                         }
                     }
                 }

@@ -316,3 +316,37 @@ def test_cfg2_full_size_properties(rb, cuda_device, crop):
         assert torch.allclose(gi2, 2 * gi, rtol=1e-4, atol=1e-4 * float(gi.abs().max()))
         del image, out1, out2, g, gi, gi2
         torch.cuda.empty_cache()
+
+
+# =============================================================================================
+# CUDA path against the reference's OWN binaries (oracle/_ref travels to the GPU box)
+# =============================================================================================
+def _reference():
+    try:
+        from oracle import refrun
+        return refrun.load()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip("reference binaries unavailable: %s" % e)
+
+
+def test_cuda_vs_reference_binaries(rb, cuda_device):
+    ref = _reference()
+    # NMS3D: bit-exact against NonMaxSuppression3DOp<CPUDevice>::Compute itself
+    for n, thr, mo in ((6000, 0.7, 1000), (2500, 0.4, 2500), (64, 0.5, 64)):
+        boxes, scores = roi3d_synth.nms_boxes(n, (128, 128, 128), seed=1200 + n)
+        if n == 64:
+            boxes[7] = [0.4, 0.4, 0.4, 0.4, 0.7, 0.7]
+            scores[7] = 3.0
+        assert np.array_equal(run_nms(rb, cuda_device, boxes, scores, mo, thr), ref.non_max_suppression_3d(boxes, scores, mo, thr))
+    # CropAndResize3D forward: bit-exact against CropAndResize3DOp::Compute; grads within tolerance
+    for case in ((2, 8, 8, 16, 64, 24, (7, 7, 7)), (2, 8, 8, 16, 256, 12, (14, 14, 14)), (3, 9, 5, 7, 1, 9, (5, 3, 4))):
+        B, H, W, D, C, n, crop = case
+        image, boxes, bidx, grads = car_inputs(1300 + C, B, H, W, D, C, n, crop)
+        t = [dev(x, cuda_device) for x in (image, boxes, bidx, grads)]
+        out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=1.5).cpu().numpy()
+        assert np.array_equal(out, ref.crop_and_resize_3d(image, boxes, bidx, crop, "trilinear", 1.5))
+        gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
+        assert rel_ok(gi, ref.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape), BWD_TOL)
+        gb = rb.crop_and_resize_3d_grad_boxes(t[3], t[0], t[1], t[2]).cpu().numpy()
+        rgb = ref.crop_and_resize_3d_grad_boxes(grads, image, boxes, bidx)
+        assert np.all(np.abs(gb - rgb) <= GB_TOL * np.abs(rgb).max() + 1e-6)

@@ -145,8 +145,10 @@ def test_grad_boxes_matches_finite_differences():
     rng = np.random.default_rng(6)
     B, H, W, D, C = 1, 9, 9, 9, 2
     img = rng.standard_normal((B, H, W, D, C), dtype=np.float32)
-    # (coordinates chosen off the integer grid: at a kink the op returns a one-sided derivative)
-    boxes = np.array([[0.11, 0.23, 0.17, 0.71, 0.83, 0.67], [0.31, 0.13, 0.21, 0.93, 0.64, 0.83]], np.float32)
+    # (coordinates chosen off the integer grid: at a kink the op returns a one-sided derivative; z1 == y1 with
+    # H == D and ph == pd, the one configuration in which the reference's depth-step slip -- (z2 - y1) * ratio_h,
+    # GB.so@0x4059 -- coincides with the true step, so all six columns are real derivatives)
+    boxes = np.array([[0.11, 0.23, 0.11, 0.71, 0.83, 0.67], [0.31, 0.13, 0.31, 0.93, 0.64, 0.83]], np.float32)
     bi = np.zeros(2, np.int32)
     crop = (3, 3, 3)
     g = rng.standard_normal((2,) + crop + (C,), dtype=np.float32)
