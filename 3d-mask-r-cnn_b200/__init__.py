@@ -19,6 +19,7 @@ from . import _lib
 _lib.load()                     # ImportError if libroi3d_b200.so is missing
 
 from . import custom_op         # noqa: E402
+from . import sharding          # noqa: E402,F401
 from .custom_op import (        # noqa: E402,F401
     InvalidArgumentError,
     crop_and_resize_3d,

@@ -194,11 +194,7 @@ def run_ours(args):
         e1.record()
         barrier()
     launches = rb.kernel_launches()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t[0])
+    ms_total = rb.sharding.max_over_ranks(e0.elapsed_time(e1))     # device time, slowest rank
     ms_step = ms_total / args.steps
     value = world * total_rois / (ms_step * 1e-3)
 
@@ -283,10 +279,7 @@ def run_ours(args):
             e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    e2e_s = rb.sharding.max_over_ranks(e2e_s)
     e2e_value = world * total_rois * e2e_steps / e2e_s
 
     line = {
