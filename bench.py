@@ -134,6 +134,7 @@ def run_ours(args):
     stream = lambda: vp(torch.cuda.current_stream().cuda_stream)   # noqa: E731
 
     ops = make_workload(seed=2002 + rank)
+    seed_is_default = rank == 0            # the ncu traffic figures were captured on rank 0's ROI set
     total_rois = BATCH * ROIS_PER_IMAGE
     # ---- device-resident state ---------------------------------------------------------------
     images = {}
@@ -218,9 +219,15 @@ def run_ours(args):
                            "crop": op["crop"][0], "n": op["n"], "ms": round(ms, 4), "alg_bytes": nbytes,
                            "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None})
     dom = max(per_op, key=lambda r: r["ms"])
-    roofline = {"bound": "hbm", "kernel": "%s P%d crop %d^3 n=%d" % (dom["op"], dom["level"], dom["crop"], dom["n"]),
+    dom_name = "%s P%d crop %d^3 n=%d" % (dom["op"], dom["level"], dom["crop"], dom["n"])
+    try:                                   # DRAM bytes per launch measured once with `ncu --set full` (profiles/README.md)
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            traffic = json.load(f).get(dom_name) if rank == 0 and seed_is_default else None
+    except Exception:  # noqa: BLE001
+        traffic = None
+    roofline = {"bound": "hbm", "kernel": dom_name,
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration of the C-ABI call"
                         + (" (zero-fill memset + scatter kernel)" if dom["op"].endswith("grad_image") else "")}
     sum_bytes = sum(r["alg_bytes"] for r in per_op)
