@@ -25,6 +25,8 @@ from .custom_op import (        # noqa: E402,F401
     crop_and_resize_3d,
     crop_and_resize_3d_grad_boxes,
     crop_and_resize_3d_grad_image,
+    deferred,
+    synchronize,
     get_option,
     kernel_launches,
     non_max_suppression_3d,

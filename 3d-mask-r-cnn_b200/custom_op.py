@@ -33,7 +33,7 @@ from . import _lib
 __all__ = [
     "InvalidArgumentError", "crop_and_resize_3d", "crop_and_resize_3d_grad_image",
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
-    "set_option", "get_option", "kernel_launches", "reset_kernel_launches",
+    "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize",
 ]
 
 METHODS = {"trilinear": 0, "nearest": 1}
@@ -67,6 +67,53 @@ def _shape(x):
     return tuple(x.shape) if hasattr(x, "shape") else tuple(np.asarray(x).shape)
 
 
+class _HostPipe:
+    """Streams of the host-buffer path: H2D copies, kernels and D2H copies run on three streams chained by
+    events, so the upload of one op's inputs overlaps the download of the previous op's result (PCIe is
+    full-duplex) and both overlap the kernels."""
+
+    _pipes = {}
+
+    def __init__(self, device):
+        self.h2d = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+        self.pending = []                  # events of D2H copies not yet waited for (deferred mode)
+        self.deferred = 0
+
+    @classmethod
+    def get(cls, device):
+        p = cls._pipes.get(device.index)
+        if p is None:
+            p = cls._pipes[device.index] = cls(device)
+        return p
+
+
+class deferred:
+    """Context manager: inside it, calls on host buffers return their (pinned) result tensors / arrays
+    immediately; the data is valid after the block exits (or after :func:`synchronize`).  Lets a step of
+    many independent ops -- the 8 + 8 CropAndResize3D nodes of PyramidROIAlign -- keep both PCIe directions
+    and the GPU busy, the way TF's executor overlaps independent nodes."""
+
+    def __enter__(self):
+        self.pipe = _HostPipe.get(_device())
+        self.pipe.deferred += 1
+        return self
+
+    def __exit__(self, *exc):
+        self.pipe.deferred -= 1
+        if self.pipe.deferred == 0:
+            synchronize()
+        return False
+
+
+def synchronize():
+    """Wait for every outstanding host-buffer result of the current device."""
+    pipe = _HostPipe.get(_device())
+    for ev in pipe.pending:
+        ev.synchronize()
+    pipe.pending.clear()
+
+
 class _Arg:
     """Brings one argument to the device; remembers whether the caller passed a host buffer."""
 
@@ -82,7 +129,15 @@ class _Arg:
             t = t.contiguous()
             if not t.is_pinned() and t.numel() * t.element_size() >= (1 << 20):
                 t = t.pin_memory()                     # pageable -> pinned staging, then one async H2D
-            self.dev = t.to(device, non_blocking=True)
+            if t.numel() * t.element_size() < (1 << 20):
+                self.dev = t.to(device, non_blocking=True)     # small: not worth a second stream
+            else:
+                pipe = _HostPipe.get(device)
+                cur = torch.cuda.current_stream(device)
+                with torch.cuda.stream(pipe.h2d):
+                    self.dev = t.to(device, non_blocking=True)
+                cur.wait_stream(pipe.h2d)              # kernels start when the upload has landed
+                self.dev.record_stream(cur)
         else:
             if t.dtype != dtype:
                 t = t.to(dtype)
@@ -93,9 +148,21 @@ def _finish(out, host, as_numpy):
     """Return `out` where the caller's inputs lived (device stays device, host gets a pinned copy)."""
     if not host:
         return out
+    pipe = _HostPipe.get(out.device)
+    if not pipe.deferred and out.numel() * out.element_size() < (1 << 20):
+        res = out.cpu()                                # small and synchronous: one blocking copy
+        return res.numpy() if as_numpy else res
     res = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-    res.copy_(out, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    pipe.d2h.wait_stream(torch.cuda.current_stream(out.device))
+    with torch.cuda.stream(pipe.d2h):
+        res.copy_(out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(pipe.d2h)
+    out.record_stream(pipe.d2h)
+    if pipe.deferred:
+        pipe.pending.append(ev)
+    else:
+        ev.synchronize()
     return res.numpy() if as_numpy else res
 
 

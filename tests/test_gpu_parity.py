@@ -350,3 +350,15 @@ def test_cuda_vs_reference_binaries(rb, cuda_device):
         gb = rb.crop_and_resize_3d_grad_boxes(t[3], t[0], t[1], t[2]).cpu().numpy()
         rgb = ref.crop_and_resize_3d_grad_boxes(grads, image, boxes, bidx)
         assert np.all(np.abs(gb - rgb) <= GB_TOL * np.abs(rgb).max() + 1e-6)
+
+
+def test_deferred_host_pipeline(rb, cuda_device):
+    """rb.deferred(): host results are valid after the block; copies and kernels of independent ops overlap."""
+    B, H, W, D, C, n, crop = 2, 8, 8, 16, 64, 12, (7, 7, 7)
+    cases = [car_inputs(800 + i, B, H, W, D, C, n, crop) for i in range(4)]
+    with rb.deferred():
+        outs = [rb.crop_and_resize_3d(im, bx, bi, crop) for im, bx, bi, _ in cases]
+        gis = [rb.crop_and_resize_3d_grad_image(g, bx, bi, im.shape) for im, bx, bi, g in cases]
+    for (im, bx, bi, g), out, gi in zip(cases, outs, gis):
+        assert np.array_equal(out, oracle.crop_and_resize_3d(im, bx, bi, crop))
+        assert rel_ok(gi, oracle.crop_and_resize_3d_grad_image(g, bx, bi, im.shape), BWD_TOL)
