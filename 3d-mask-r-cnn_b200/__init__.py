@@ -30,6 +30,10 @@ from .custom_op import (        # noqa: E402,F401
     get_option,
     kernel_launches,
     non_max_suppression_3d,
+    non_max_suppression_3d_batched,
+    non_max_suppression_3d_graph,
+    non_max_suppression_3d_per_class,
+    pyramid_roi_align_3d,
     reset_kernel_launches,
     set_option,
 )

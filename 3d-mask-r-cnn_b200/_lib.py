@@ -29,8 +29,9 @@ NVCC_FLAGS = [
 
 EXPORTS = [
     "roi3d_version", "roi3d_strerror", "roi3d_last_cuda_error",
-    "roi3d_nms3d_workspace_bytes", "roi3d_nms3d",
+    "roi3d_nms3d_workspace_bytes", "roi3d_nms3d", "roi3d_nms3d_batched_workspace_bytes", "roi3d_nms3d_batched",
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
+    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad",
     "roi3d_set_option", "roi3d_get_option", "roi3d_kernel_launches", "roi3d_reset_kernel_launches",
 ]
 
@@ -82,12 +83,20 @@ def _declare(lib):
     lib.roi3d_nms3d_workspace_bytes.argtypes = [i]
     lib.roi3d_nms3d.restype = i
     lib.roi3d_nms3d.argtypes = [vp, vp, i, i, f, vp, vp, vp, sz, vp]
+    lib.roi3d_nms3d_batched_workspace_bytes.restype = sz
+    lib.roi3d_nms3d_batched_workspace_bytes.argtypes = [i, i]
+    lib.roi3d_nms3d_batched.restype = i
+    lib.roi3d_nms3d_batched.argtypes = [vp, vp, vp, i, i, i, f, vp, vp, vp, sz, vp]
     lib.roi3d_car3d_fwd.restype = i
     lib.roi3d_car3d_fwd.argtypes = [vp, i, i, i, i, i, vp, vp, i, i, i, i, i, f, vp, vp]
     lib.roi3d_car3d_grad_image.restype = i
     lib.roi3d_car3d_grad_image.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp, vp]
     lib.roi3d_car3d_grad_boxes.restype = i
     lib.roi3d_car3d_grad_boxes.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, i, i, i, vp, vp]
+    lib.roi3d_pyramid_roi_align_fwd.restype = i
+    lib.roi3d_pyramid_roi_align_fwd.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp]
+    lib.roi3d_pyramid_roi_align_grad.restype = i
+    lib.roi3d_pyramid_roi_align_grad.argtypes = [vp, vp, vp, i, i, vp, i, vp, i, i, i, vp]
     lib.roi3d_set_option.restype = i
     lib.roi3d_set_option.argtypes = [ctypes.c_char_p, i]
     lib.roi3d_get_option.restype = i

@@ -64,7 +64,21 @@ int roi3d_get_option(const char *name, int *value) {
     return ROI3D_OK;
 }
 
-size_t roi3d_nms3d_workspace_bytes(int n) { return nms3d_workspace_bytes(n); }
+size_t roi3d_nms3d_workspace_bytes(int n) { return nms3d_workspace_bytes(n, 1); }
+size_t roi3d_nms3d_batched_workspace_bytes(int n_max, int segments) { return nms3d_workspace_bytes(n_max, segments); }
+
+int roi3d_nms3d_batched(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n_max,
+                        int max_out, float iou_thr, int *keep_idx, int *keep_count, void *workspace,
+                        size_t workspace_bytes, roi3d_stream_t stream)
+{
+    if (segments < 0 || n_max < 0 || max_out < 0 || !keep_count) return ROI3D_EINVAL;
+    if (!(iou_thr >= 0.0f && iou_thr <= 1.0f)) return ROI3D_EINVAL;
+    if (segments == 0) return ROI3D_OK;
+    if (!seg_offsets) return ROI3D_EINVAL;
+    if (n_max > 0 && max_out > 0 && (!boxes || !scores || !keep_idx)) return ROI3D_EINVAL;
+    return launch_nms3d(boxes, scores, seg_offsets, segments, n_max, max_out, iou_thr, keep_idx, keep_count, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 
 int roi3d_nms3d(const float *boxes, const float *scores, int n, int max_out, float iou_thr,
                 int *keep_idx, int *keep_count, void *workspace, size_t workspace_bytes,
@@ -73,7 +87,7 @@ int roi3d_nms3d(const float *boxes, const float *scores, int n, int max_out, flo
     if (n < 0 || max_out < 0 || !keep_count) return ROI3D_EINVAL;
     if (!(iou_thr >= 0.0f && iou_thr <= 1.0f)) return ROI3D_EINVAL;       // "iou_threshold must be in [0, 1]"
     if (n > 0 && max_out > 0 && (!boxes || !scores || !keep_idx)) return ROI3D_EINVAL;
-    return launch_nms3d(boxes, scores, n, max_out, iou_thr, keep_idx, keep_count, workspace, workspace_bytes,
+    return launch_nms3d(boxes, scores, nullptr, 0, n, max_out, iou_thr, keep_idx, keep_count, workspace, workspace_bytes,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -131,6 +145,55 @@ int roi3d_car3d_grad_boxes(const float *grads, const float *image, int B, int H,
     if (!grads || !image || !boxes || !box_ind || !grad_boxes) return ROI3D_EINVAL;
     if (!geom_supported(g)) return ROI3D_EUNSUPPORTED;
     return launch_car3d_grad_boxes(grads, image, boxes, box_ind, g, grad_boxes, static_cast<cudaStream_t>(stream));
+}
+
+static int pyramid_check(const int level_shapes[4][3], int B, int C, const float *boxes, int rois_per_image,
+                         const float image_shape[3], int ph, int pw, int pd)
+{
+    if (!level_shapes || !image_shape || B <= 0 || C <= 0 || rois_per_image < 0 || ph <= 0 || pw <= 0 || pd <= 0) return ROI3D_EINVAL;
+    if (rois_per_image > 0 && !boxes) return ROI3D_EINVAL;
+    for (int l = 0; l < 4; ++l) {
+        if (level_shapes[l][0] <= 0 || level_shapes[l][1] <= 0 || level_shapes[l][2] <= 0) return ROI3D_EINVAL;
+        if ((long long)level_shapes[l][0] * level_shapes[l][1] * level_shapes[l][2] * C >= (1ll << 31)) return ROI3D_EUNSUPPORTED;
+    }
+    if (C % 4 != 0 || ph > 64 || pw > 64 || pd > 64) return ROI3D_EUNSUPPORTED;     // the fused path is the plane kernel
+    return ROI3D_OK;
+}
+
+int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                const float *boxes, int rois_per_image, const float image_shape[3],
+                                int ph, int pw, int pd, float *pooled, roi3d_stream_t stream)
+{
+    const int rc = pyramid_check(level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd);
+    if (rc != ROI3D_OK) return rc;
+    if (rois_per_image == 0) return ROI3D_OK;
+    if (!feature_maps || !pooled) return ROI3D_EINVAL;
+    int H[4], W[4], D[4];
+    for (int l = 0; l < 4; ++l) {
+        if (!feature_maps[l] || (reinterpret_cast<uintptr_t>(feature_maps[l]) & 15)) return ROI3D_EINVAL;
+        H[l] = level_shapes[l][0]; W[l] = level_shapes[l][1]; D[l] = level_shapes[l][2];
+    }
+    if (reinterpret_cast<uintptr_t>(pooled) & 15) return ROI3D_EINVAL;
+    return launch_pyramid_fwd(feature_maps, H, W, D, B, C, boxes, rois_per_image, image_shape[0], image_shape[1],
+                              image_shape[2], ph, pw, pd, pooled, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], const int level_shapes[4][3], int B, int C,
+                                 const float *boxes, int rois_per_image, const float image_shape[3],
+                                 int ph, int pw, int pd, roi3d_stream_t stream)
+{
+    const int rc = pyramid_check(level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd);
+    if (rc != ROI3D_OK) return rc;
+    if (!grad_maps) return ROI3D_EINVAL;
+    if (rois_per_image > 0 && !grads) return ROI3D_EINVAL;
+    int H[4], W[4], D[4];
+    for (int l = 0; l < 4; ++l) {
+        if (!grad_maps[l] || (reinterpret_cast<uintptr_t>(grad_maps[l]) & 15)) return ROI3D_EINVAL;
+        H[l] = level_shapes[l][0]; W[l] = level_shapes[l][1]; D[l] = level_shapes[l][2];
+    }
+    if (reinterpret_cast<uintptr_t>(grads) & 15) return ROI3D_EINVAL;
+    return launch_pyramid_grad(grads, grad_maps, H, W, D, B, C, boxes, rois_per_image, image_shape[0], image_shape[1],
+                               image_shape[2], ph, pw, pd, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -147,6 +147,40 @@ struct __align__(16) OutEntry {             // per output (y, x) of the current 
     float xl, yl;
 };
 
+// ---- fused PyramidROIAlign -------------------------------------------------------
+// In pyramid mode a launch serves all four levels: every CTA clips its ROI, routes it to a level with the
+// reference's formula (PyramidROIAlign.call, core/models.py:615-649) and then runs the ordinary plane-staged crop on
+// that level's map, writing the crop at the ROI's original position (no where / gather_nd / concat / top_k glue).
+struct PyrParams {
+    const float *image[4];      // P2..P5 (forward) -- or grad images (backward)
+    int H[4], W[4], D[4];       // level shapes [B, H_l, W_l, D_l, C]
+    float imH, imW, imD;        // image_shape from image_meta (routing and the z min-size rule)
+    int rois_per_image;         // boxes are [B, R, 6]; box_index = roi / R
+};
+
+struct PyrRoute { float box[6]; int level; };
+
+// tf.clip_by_value, min sizes, level = clamp(4 + round(log2(cbrt(h*w*d) / (224 / cbrt(H*W*D)))), 2, 5) in fp32
+__device__ __forceinline__ PyrRoute pyr_route(const float *b6, const PyrParams &P) {
+    PyrRoute r;
+    float y1 = fminf(fmaxf(b6[0], 0.f), 1.f), x1 = fminf(fmaxf(b6[1], 0.f), 1.f), z1 = fminf(fmaxf(b6[2], 0.f), 1.f);
+    float y2 = fminf(fmaxf(b6[3], 0.f), 1.f), x2 = fminf(fmaxf(b6[4], 0.f), 1.f), z2 = fminf(fmaxf(b6[5], 0.f), 1.f);
+    y2 = fmaxf(y2, __fadd_rn(y1, 1e-6f));
+    x2 = fmaxf(x2, __fadd_rn(x1, 1e-6f));
+    z2 = fmaxf(z2, __fadd_rn(z1, __fdiv_rn(1.0f, fmaxf(P.imD, 1.0f))));
+    r.box[0] = y1; r.box[1] = x1; r.box[2] = z1; r.box[3] = y2; r.box[4] = x2; r.box[5] = z2;
+    const float vol = __fmul_rn(__fmul_rn(__fsub_rn(y2, y1), __fsub_rn(x2, x1)), __fsub_rn(z2, z1));
+    const float area = __fmul_rn(__fmul_rn(P.imH, P.imW), P.imD);
+    const float ratio = __fdiv_rn(powf(vol, 1.0f / 3.0f), __fdiv_rn(224.0f, powf(area, 1.0f / 3.0f)));
+    const float lvl = __fdiv_rn(logf(ratio), logf(2.0f));
+    r.level = min(5, max(2, 4 + (int)rintf(lvl)));
+    return r;
+}
+
+__device__ __forceinline__ float4 scrub4(const float4 v) {       // tf.where(is_finite(x), x, 0), core/models.py:683
+    return make_float4(isfinite(v.x) ? v.x : 0.f, isfinite(v.y) ? v.y : 0.f, isfinite(v.z) ? v.z : 0.f, isfinite(v.w) ? v.w : 0.f);
+}
+
 __device__ __forceinline__ float4 sel4(bool bad, const float4 a, const float4 b) {
     return make_float4(bad ? a.x : b.x, bad ? a.y : b.y, bad ? a.z : b.z, bad ? a.w : b.w);
 }
@@ -154,11 +188,11 @@ __device__ __forceinline__ float4 sel4(bool bad, const float4 a, const float4 b)
 // ---------------------------------------------------------------------------------
 // forward.  V = float4 channel groups per thread (the chunk is cl * V * 4 channels).
 // ---------------------------------------------------------------------------------
-template <int V>
+template <int V, bool PYR>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                        const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
-                       float *__restrict__ crops)
+                       float *__restrict__ crops, const PyrParams P)
 {
     constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,8 +206,25 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const int chunk = bid % L.chunks; bid /= L.chunks;
     const int ks = bid % L.ksplits;
     const int b = bid / L.ksplits;
-    if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
-    __syncthreads();
+    __shared__ int s_level;
+    if constexpr (PYR) {
+        if (threadIdx.x == 0) {
+            float b6[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) b6[q] = __ldg(boxes + (size_t)b * 6 + q);
+            const PyrRoute r = pyr_route(b6, P);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) S.box[q] = r.box[q];
+            s_level = r.level - 2;
+        }
+        __syncthreads();
+        const int lv = s_level;
+        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
+        image = P.image[lv];
+    } else {
+        if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
+        __syncthreads();
+    }
     build_axis_tables(S, g);
     build_y_tiles(S, g, L.zcap);
 
@@ -186,7 +237,8 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
 #pragma unroll
     for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
-    const float *img = image + (long long)__ldg(box_index + b) * g.H * sH + c4 * 4;
+    const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
+    const float *img = image + (long long)bimg * g.H * sH + c4 * 4;
     float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float4 ext4 = make_float4(ext, ext, ext, ext);
     const float z1 = S.box[2], z2 = S.box[5];
@@ -282,7 +334,9 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
                         const float4 tlv = lds128(a_tl + vo), trv = lds128(a_tr + vo);
                         const float4 blv = lds128(a_bl + vo), brv = lds128(a_br + vo);
                         const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
-                        st_stream4(o + v * vstep, sel4(bad, ext4, lerp_rn(top, bot, yl)));
+                        float4 res = sel4(bad, ext4, lerp_rn(top, bot, yl));
+                        if constexpr (PYR) res = scrub4(res);
+                        st_stream4(o + v * vstep, res);
                     }
                 }
             }
@@ -338,11 +392,11 @@ __device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, c
     __syncthreads();
 }
 
-template <int V>
+template <int V, bool PYR>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
-                              float *__restrict__ grad_image)
+                              float *__restrict__ grad_image, const PyrParams P)
 {
     constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -355,8 +409,25 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     const int chunk = bid % L.chunks; bid /= L.chunks;
     const int ks = bid % L.ksplits;
     const int b = bid / L.ksplits;
-    if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
-    __syncthreads();
+    __shared__ int s_level;
+    if constexpr (PYR) {
+        if (threadIdx.x == 0) {
+            float b6[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) b6[q] = __ldg(boxes + (size_t)b * 6 + q);
+            const PyrRoute r = pyr_route(b6, P);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) S.box[q] = r.box[q];
+            s_level = r.level - 2;
+        }
+        __syncthreads();
+        const int lv = s_level;
+        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
+        grad_image = const_cast<float *>(P.image[lv]);
+    } else {
+        if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
+        __syncthreads();
+    }
     build_axis_tables(S, g);
     const AxisTab &Y = S.ax[0], &X = S.ax[1];
     const int cl = L.cl;
@@ -371,7 +442,8 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
 #pragma unroll
     for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const long long sW = (long long)g.D * g.C, sH = (long long)g.W * g.D * g.C;
-    float *img = grad_image + (long long)__ldg(box_ind + b) * g.H * sH + c4 * 4;
+    const int bimg = PYR ? b / P.rois_per_image : __ldg(box_ind + b);
+    float *img = grad_image + (long long)bimg * g.H * sH + c4 * 4;
     const float *gcrop = grads + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float z1 = S.box[2], z2 = S.box[5];
     const float zscale = axis_scale(z1, z2, g.D, g.pd);
@@ -497,8 +569,8 @@ static int pick_ksplits(const CarGeom &g, int chunks) {
     return (int)ks;
 }
 
-int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
-                           float ext, float *crops, cudaStream_t stream)
+static int launch_fwd_plane_impl(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                                 float ext, float *crops, const PyrParams *pyr, cudaStream_t stream)
 {
     PlaneLaunch L;
     int V;
@@ -517,18 +589,25 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
     }
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
-    auto kern = (V == 2) ? car3d_fwd_plane_kernel<2> : car3d_fwd_plane_kernel<1>;
+    auto kern = pyr ? ((V == 2) ? car3d_fwd_plane_kernel<2, true> : car3d_fwd_plane_kernel<1, true>)
+                    : ((V == 2) ? car3d_fwd_plane_kernel<2, false> : car3d_fwd_plane_kernel<1, false>);
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops);
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, pyr ? *pyr : PyrParams{});
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
 
-int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream)
+int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                           float ext, float *crops, cudaStream_t stream)
+{
+    return launch_fwd_plane_impl(image, boxes, box_index, g, ext, crops, nullptr, stream);
+}
+
+static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
+                                  float *grad_image, const PyrParams *pyr, cudaStream_t stream)
 {
     PlaneLaunch L;
     int V;
@@ -546,14 +625,52 @@ int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const 
     }
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
-    auto kern = (V == 2) ? car3d_grad_image_plane_kernel<2> : car3d_grad_image_plane_kernel<1>;
+    auto kern = pyr ? ((V == 2) ? car3d_grad_image_plane_kernel<2, true> : car3d_grad_image_plane_kernel<1, true>)
+                    : ((V == 2) ? car3d_grad_image_plane_kernel<2, false> : car3d_grad_image_plane_kernel<1, false>);
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image);
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{});
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
+}
+
+int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
+                                  float *grad_image, cudaStream_t stream)
+{
+    return launch_grad_plane_impl(grads, boxes, box_ind, g, grad_image, nullptr, stream);
+}
+
+// ---- fused PyramidROIAlign entry points (geometry g: B, C, n = B * R, crop; H/W/D = the largest level, for sizing) ----
+int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
+                       const float *boxes, int rois_per_image, float imH, float imW, float imD,
+                       int ph, int pw, int pd, float *crops, cudaStream_t stream)
+{
+    PyrParams P;
+    for (int l = 0; l < 4; ++l) { P.image[l] = images[l]; P.H[l] = H[l]; P.W[l] = W[l]; P.D[l] = D[l]; }
+    P.imH = imH; P.imW = imW; P.imD = imD; P.rois_per_image = rois_per_image;
+    int wmax = 1;
+    for (int l = 0; l < 4; ++l) wmax = max(wmax, W[l]);
+    const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
+    return launch_fwd_plane_impl(nullptr, boxes, nullptr, g, 0.0f, crops, &P, stream);
+}
+
+int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],
+                        int B, int C, const float *boxes, int rois_per_image, float imH, float imW, float imD,
+                        int ph, int pw, int pd, cudaStream_t stream)
+{
+    PyrParams P;
+    for (int l = 0; l < 4; ++l) {
+        P.image[l] = grad_images[l]; P.H[l] = H[l]; P.W[l] = W[l]; P.D[l] = D[l];
+        ROI3D_CUDA_TRY(cudaMemsetAsync(grad_images[l], 0, sizeof(float) * (size_t)B * H[l] * W[l] * D[l] * C, stream));
+    }
+    P.imH = imH; P.imW = imW; P.imD = imD; P.rois_per_image = rois_per_image;
+    int wmax = 1;
+    for (int l = 0; l < 4; ++l) wmax = max(wmax, W[l]);
+    const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
+    if (g.n == 0) return ROI3D_OK;
+    return launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream);
 }
 
 }  // namespace roi3d

@@ -120,8 +120,14 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
                                   float *grad_image, cudaStream_t stream);
-size_t nms3d_workspace_bytes(int n);
-int launch_nms3d(const float *boxes, const float *scores, int n, int max_out, float thr,
-                 int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);
+int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
+                       const float *boxes, int rois_per_image, float imH, float imW, float imD,
+                       int ph, int pw, int pd, float *crops, cudaStream_t stream);
+int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],
+                        int B, int C, const float *boxes, int rois_per_image, float imH, float imW, float imD,
+                        int ph, int pw, int pd, cudaStream_t stream);
+size_t nms3d_workspace_bytes(int n, int segments);
+int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n, int max_out,
+                 float thr, int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace roi3d

@@ -35,6 +35,20 @@ struct __align__(16) SBox {          // canonical sorted box, 32 bytes
     float xmax, zmax, vol, pad;
 };
 
+// One launch can run many independent NMS problems ("segments": the images of a batch in ProposalLayer's
+// batch_slice, core/models.py:487-490, or the classes of DetectionLayer's per-class NMS).  Segment z covers the input
+// boxes [offsets[z], offsets[z+1]) and owns workspace slices of `stride` boxes; offsets == nullptr means a single
+// problem of n boxes.  Indices are local to the segment.
+struct NmsSeg {
+    const int *offsets;
+    int n;
+    int stride;
+};
+__device__ __forceinline__ int seg_begin(const NmsSeg &g, int z) { return g.offsets ? __ldg(g.offsets + z) : 0; }
+__device__ __forceinline__ int seg_size(const NmsSeg &g, int z) {
+    return g.offsets ? __ldg(g.offsets + z + 1) - __ldg(g.offsets + z) : g.n;
+}
+
 __device__ __forceinline__ unsigned score_key(float s) {
     // ascending unsigned key <=> descending score; invalid candidates -> 0xFFFFFFFF.
     // Candidate rule of the reference: score > -FLT_MAX (NaN fails it).  -0.0 == +0.0.
@@ -54,9 +68,19 @@ constexpr int RS_THREADS = RS_ITILE * RS_JSPLIT;
 constexpr int RS_KTILE = 4096;      // keys staged per shared-memory tile
 
 __global__ void __launch_bounds__(RS_THREADS)
-nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int n,
+nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, NmsSeg seg,
                      int *__restrict__ sorted_idx, SBox *__restrict__ sboxes, int *__restrict__ nvalid_out)
 {
+    const int z = blockIdx.y, n = seg_size(seg, z);
+    if (blockIdx.x > 0 && blockIdx.x * RS_ITILE >= n) return;          // CTA-uniform; CTA 0 still publishes nvalid
+    {
+        const int base = seg_begin(seg, z);
+        boxes += (size_t)base * 6;
+        scores += base;
+        sorted_idx += (size_t)z * seg.stride;
+        sboxes += (size_t)z * seg.stride;
+        nvalid_out += z;
+    }
     __shared__ __align__(16) unsigned s_keys[RS_KTILE];
     __shared__ int s_rank[RS_ITILE];
     __shared__ int s_valid;
@@ -153,11 +177,15 @@ __device__ __forceinline__ bool iou_ge(const float4 a0, const float4 a1, const f
 }
 
 __global__ void __launch_bounds__(MK_WARPS * 32)
-nms_mask_kernel(const SBox *__restrict__ sboxes, int n, int pitch_words, float thr,
+nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, float thr,
                 unsigned *__restrict__ mask)
 {
     __shared__ float4 s_rows[MK_ROWS * 2];
+    const int z = blockIdx.z, n = seg_size(seg, z);
     const int i0 = blockIdx.y * MK_ROWS;
+    if (i0 >= n || blockIdx.x * MK_WARPS * 32 >= n) return;             // CTA-uniform
+    sboxes += (size_t)z * seg.stride;
+    mask += (size_t)z * seg.stride * pitch_words;
     const int w0 = blockIdx.x * MK_WARPS;
     // only words that contain some column j >= i0 are ever read by the scan
     if ((w0 + MK_WARPS) * 32 <= i0) return;
@@ -233,7 +261,7 @@ __device__ __forceinline__ void sc_prefetch(unsigned *dst, float *vol, int *sidx
 
 __global__ void __launch_bounds__(SC_THREADS)
 nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *__restrict__ sboxes,
-                const int *__restrict__ sorted_idx, const int *__restrict__ nvalid_p,
+                const int *__restrict__ sorted_idx, const int *__restrict__ nvalid_p, int seg_stride,
                 int max_out, float thr, int *__restrict__ keep_idx, int *__restrict__ keep_count)
 {
     extern __shared__ unsigned s_dyn[];
@@ -243,6 +271,15 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
     int *s_sidx = reinterpret_cast<int *>(s_vol + 2 * SC_SB);             // 2 x SC_SB
     __shared__ int s_krows[SC_SB];                             // kept rows of the current super-chunk
     __shared__ int s_nk, s_nsel, s_fill, s_done;
+    {
+        const size_t z = blockIdx.x;                                   // one CTA per segment
+        mask += z * seg_stride * pitch_words;
+        sboxes += z * seg_stride;
+        sorted_idx += z * seg_stride;
+        nvalid_p += z;
+        keep_idx += z * max_out;
+        keep_count += z;
+    }
     const int nvalid = *nvalid_p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (nvalid + 31) >> 5;
@@ -371,46 +408,51 @@ struct NmsLayout {
     size_t off_sidx, off_sboxes, off_nvalid, off_mask, total;
 };
 
-static NmsLayout nms_layout(int n) {
+static NmsLayout nms_layout(int n, int segments) {
     NmsLayout L;
     const int words = (n + 31) / 32;
+    const size_t S = (size_t)(segments > 0 ? segments : 1);
     L.pitch_words = (int)align_up((size_t)(words > 0 ? words : 1), 32);   // 128-byte rows
     size_t off = 0;
-    L.off_nvalid = off; off += 256;
-    L.off_sidx = off;   off += align_up(sizeof(int) * (size_t)n, 256);
-    L.off_sboxes = off; off += align_up(sizeof(SBox) * (size_t)n, 256);
-    L.off_mask = off;   off += align_up(sizeof(unsigned) * (size_t)n * L.pitch_words, 256);
+    L.off_nvalid = off; off += align_up(sizeof(int) * S, 256);
+    L.off_sidx = off;   off += align_up(sizeof(int) * S * n, 256);
+    L.off_sboxes = off; off += align_up(sizeof(SBox) * S * n, 256);
+    L.off_mask = off;   off += align_up(sizeof(unsigned) * S * n * L.pitch_words, 256);
     L.total = off;
     return L;
 }
 
-size_t nms3d_workspace_bytes(int n) { return n <= 0 ? 256 : nms_layout(n).total; }
+size_t nms3d_workspace_bytes(int n, int segments) { return n <= 0 ? 256 : nms_layout(n, segments).total; }
 
-int launch_nms3d(const float *boxes, const float *scores, int n, int max_out, float thr,
-                 int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream)
+// segments == 0: one problem of n boxes (seg_offsets ignored); else `segments` problems of at most n boxes each
+int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n, int max_out,
+                 float thr, int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream)
 {
+    const int S = segments > 0 ? segments : 1;
     if (n <= 0 || max_out <= 0) {
-        ROI3D_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int), stream));
+        ROI3D_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int) * S, stream));
         return ROI3D_OK;
     }
-    const NmsLayout L = nms_layout(n);
+    const NmsLayout L = nms_layout(n, S);
     if (ws == nullptr || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return ROI3D_EWORKSPACE;
     if ((size_t)L.pitch_words * sizeof(unsigned) > 128 * 1024) return ROI3D_EUNSUPPORTED;   // > 1 M boxes
+    if (S > 65535) return ROI3D_EUNSUPPORTED;
     char *base = static_cast<char *>(ws);
     int *nvalid = reinterpret_cast<int *>(base + L.off_nvalid);
     int *sidx = reinterpret_cast<int *>(base + L.off_sidx);
     SBox *sboxes = reinterpret_cast<SBox *>(base + L.off_sboxes);
     unsigned *mask = reinterpret_cast<unsigned *>(base + L.off_mask);
+    const NmsSeg seg{segments > 0 ? seg_offsets : nullptr, n, n};
 
-    nms_rank_sort_kernel<<<(n + RS_ITILE - 1) / RS_ITILE, RS_THREADS, 0, stream>>>(boxes, scores, n, sidx, sboxes, nvalid);
+    nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, scores, seg, sidx, sboxes, nvalid);
     ROI3D_LAUNCH_CHECK();
     const int words = (n + 31) / 32;
-    dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS);
-    nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, n, L.pitch_words, thr, mask);
+    dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
+    nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, mask);
     ROI3D_LAUNCH_CHECK();
     const size_t smem = ((size_t)L.pitch_words + 2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
     ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<<<1, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, max_out, thr,
+    nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr,
                                                     keep_idx, keep_count);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;

@@ -33,6 +33,8 @@ from . import _lib
 __all__ = [
     "InvalidArgumentError", "crop_and_resize_3d", "crop_and_resize_3d_grad_image",
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
+    "non_max_suppression_3d_batched", "non_max_suppression_3d_per_class", "non_max_suppression_3d_graph",
+    "pyramid_roi_align_3d", "PyramidROIAlign3DFunction",
     "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize",
 ]
 
@@ -215,6 +217,78 @@ def non_max_suppression_3d(boxes, scores, max_output_size, iou_threshold=0.5, na
     return _finish(keep[:m], host, b.numpy)
 
 
+def non_max_suppression_3d_batched(boxes, scores, seg_offsets, max_output_size, iou_threshold=0.5):
+    """`S` independent 3-D NMS problems in one set of launches.
+
+    ``boxes [T,6]``, ``scores [T]`` hold the segments back to back; ``seg_offsets`` is an ascending int sequence of
+    length S+1 (host list / numpy / tensor).  Returns a list of S int32 tensors with indices LOCAL to each segment,
+    each bit-identical to :func:`non_max_suppression_3d` on that segment alone.  This is what replaces the
+    per-image ``utils.batch_slice`` loop around the op in ProposalLayer (core/models.py:487-490) and a per-class
+    loop in DetectionLayer.
+    """
+    bs, ss = _shape(boxes), _shape(scores)
+    _require(len(bs) == 2, "boxes must be 2-D")
+    _require(bs[1] == 6, "boxes must have 6 columns")
+    _require(len(ss) == 1, "scores must be 1-D")
+    _require(ss[0] == bs[0], "scores has incompatible shape")
+    thr = float(iou_threshold)
+    _require(0.0 <= thr <= 1.0, "iou_threshold must be in [0, 1]")
+    offs = np.asarray(seg_offsets.cpu() if isinstance(seg_offsets, torch.Tensor) else seg_offsets, dtype=np.int64)
+    _require(offs.ndim == 1 and len(offs) >= 1, "seg_offsets must be 1-D with at least one element")
+    _require(offs[0] >= 0 and offs[-1] <= bs[0] and np.all(np.diff(offs) >= 0), "seg_offsets must ascend within [0, N]")
+    S, max_out = len(offs) - 1, max(int(max_output_size), 0)
+    dev = _device()
+    b, s = _Arg(boxes, torch.float32, dev), _Arg(scores, torch.float32, dev)
+    if S == 0:
+        return []
+    n_max = int(np.diff(offs).max())
+    host = b.host or s.host
+    lib = _lib.load()
+    keep = torch.empty((S, max(max_out, 1)), dtype=torch.int32, device=dev)
+    count = torch.zeros(S, dtype=torch.int32, pin_memory=True)
+    if n_max > 0 and max_out > 0:
+        d_offs = torch.as_tensor(offs.astype(np.int32)).to(dev, non_blocking=True)
+        nbytes = lib.roi3d_nms3d_batched_workspace_bytes(n_max, S)
+        ws = _workspace(nbytes, dev)
+        _lib.check(lib.roi3d_nms3d_batched(_ptr(b.dev), _ptr(s.dev), _ptr(d_offs), S, n_max, max_out, thr, _ptr(keep),
+                                           _ptr(count), _ptr(ws), ws.numel(), _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+    out = [keep[z, :int(count[z])] for z in range(S)]
+    if host:
+        out = [t.cpu() for t in out]
+        if b.numpy:
+            out = [t.numpy() for t in out]
+    return out
+
+
+def non_max_suppression_3d_per_class(boxes, scores, class_ids, max_output_size, iou_threshold=0.5):
+    """Per-class 3-D NMS (the upstream DetectionLayer design, BASELINE cfg3): boxes of different classes never
+    suppress each other.  Returns ``(keep, classes)``: for each class present (ascending id) the ORIGINAL indices
+    kept, in selection order.  Grouping is a stable device sort by class id; the NMS itself is one batched call."""
+    dev = _device()
+    c = _Arg(class_ids, torch.int64, dev)
+    b, s = _Arg(boxes, torch.float32, dev), _Arg(scores, torch.float32, dev)
+    _require(c.dev.dim() == 1 and c.dev.shape[0] == b.dev.shape[0], "class_ids has incompatible shape")
+    order = torch.sort(c.dev, stable=True).indices
+    classes, counts = torch.unique_consecutive(c.dev[order], return_counts=True)
+    offs = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+    kept = non_max_suppression_3d_batched(b.dev[order], s.dev[order], offs, max_output_size, iou_threshold)
+    keep = [order[int(offs[z]):int(offs[z + 1])][k.long()].to(torch.int32) for z, k in enumerate(kept)]
+    if b.host:
+        keep = [k.cpu().numpy() if b.numpy else k.cpu() for k in keep]
+    return keep, classes.cpu().tolist()
+
+
+def non_max_suppression_3d_graph(boxes, scores, threshold, max_boxes):
+    """Mirror of ``utils.non_max_suppression_3d_graph`` (core/utils.py:467-503): ``(selected_boxes [M,6],
+    keep_indices [M])`` with python-scalar threshold / limit."""
+    keep = non_max_suppression_3d(boxes, scores, int(max_boxes), float(threshold))
+    if isinstance(keep, np.ndarray):
+        return np.asarray(boxes, np.float32)[keep], keep
+    src = boxes if isinstance(boxes, torch.Tensor) else torch.as_tensor(boxes)
+    return src.to(torch.float32)[keep.long().to(src.device)], keep
+
+
 # ---------------------------------------------------------------------------------------
 # CropAndResize3D family
 # ---------------------------------------------------------------------------------------
@@ -367,6 +441,61 @@ def crop_and_resize_3d_grad_boxes(grads, image, boxes, box_ind, method_name="tri
     host = g.host or im.host or b.host or bi.host
     out = _grad_boxes_device(g.dev, im.dev, b.dev, bi.dev)
     return _finish(out, host, g.numpy)
+
+
+# ---------------------------------------------------------------------------------------
+# fused PyramidROIAlign3D
+# ---------------------------------------------------------------------------------------
+def _pyr_args(feature_maps, image_shape):
+    assert len(feature_maps) == 4, "feature_maps = [P2, P3, P4, P5]"
+    shapes = (ctypes.c_int * 12)(*[int(d) for fm in feature_maps for d in fm.shape[1:4]])
+    ptrs = (ctypes.c_void_p * 4)(*[fm.data_ptr() for fm in feature_maps])
+    ishape = (ctypes.c_float * 3)(*[float(v) for v in image_shape])
+    return ptrs, shapes, ishape
+
+
+class PyramidROIAlign3DFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, boxes, image_shape, pool_shape, p2, p3, p4, p5):
+        fms = [t.contiguous() for t in (p2, p3, p4, p5)]
+        boxes = boxes.contiguous()
+        B, R = boxes.shape[:2]
+        C = fms[0].shape[4]
+        out = torch.empty((B, R) + tuple(pool_shape) + (C,), dtype=torch.float32, device=boxes.device)
+        ptrs, shapes, ishape = _pyr_args(fms, image_shape)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd(ptrs, shapes, B, C, _ptr(boxes), R, ishape, pool_shape[0],
+                                                           pool_shape[1], pool_shape[2], _ptr(out), _stream_ptr()))
+        ctx.save_for_backward(boxes)
+        ctx.meta = (tuple(image_shape), tuple(pool_shape), [tuple(t.shape) for t in fms])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (boxes,) = ctx.saved_tensors
+        image_shape, pool_shape, shapes = ctx.meta
+        grad = grad.contiguous()
+        B, R = boxes.shape[:2]
+        gms = [torch.empty(sh, dtype=torch.float32, device=grad.device) for sh in shapes]
+        ptrs, cshapes, ishape = _pyr_args(gms, image_shape)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_grad(_ptr(grad), ptrs, cshapes, B, shapes[0][4], _ptr(boxes), R, ishape,
+                                                            pool_shape[0], pool_shape[1], pool_shape[2], _stream_ptr()))
+        return (None, None, None) + tuple(gms)
+
+
+def pyramid_roi_align_3d(boxes, image_shape, feature_maps, pool_shape):
+    """Fused ``PyramidROIAlign(pool_shape)([boxes, image_meta, P2, P3, P4, P5])`` (core/models.py:604-685).
+
+    ``boxes [B,R,6]`` normalized, ``image_shape = (H, W, D)`` of the input volume, ``feature_maps`` = four CUDA
+    tensors ``[B,H_l,W_l,D_l,C]``.  Returns ``[B,R,ph,pw,pd,C]`` in the boxes' order; differentiable w.r.t. the
+    feature maps (boxes are stop_gradient'ed upstream, core/models.py:660)."""
+    dev = _device()
+    for t in list(feature_maps) + [boxes]:
+        if not (isinstance(t, torch.Tensor) and t.device.type == "cuda" and t.dtype == torch.float32):
+            raise InvalidArgumentError("pyramid_roi_align_3d takes float32 CUDA tensors")
+    _require(boxes.dim() == 3 and boxes.shape[2] == 6, "boxes must be [B, R, 6]")
+    _require(all(fm.dim() == 5 and fm.shape[0] == boxes.shape[0] for fm in feature_maps), "feature maps must be [B,H,W,D,C]")
+    del dev
+    return PyramidROIAlign3DFunction.apply(boxes, tuple(image_shape), tuple(int(v) for v in pool_shape), *feature_maps)
 
 
 # ---------------------------------------------------------------------------------------

@@ -233,6 +233,42 @@ def run_ours(args):
     sum_bytes = sum(r["alg_bytes"] for r in per_op)
     step_gbs = sum_bytes / (ms_step * 1e-3) / 1e9
 
+    # ---- the same step through the fused PyramidROIAlign3D entry points: 2 + 2 launches ----
+    boxes_br = np.stack([roi3d_synth.rois(ROIS_PER_IMAGE, VOLUME, (2002 + rank) * 131 + b) for b in range(BATCH)])
+    d_boxes_br = torch.from_numpy(boxes_br).to(dev)
+    fms = [images[lv] for lv in roi3d_synth.LEVELS]
+    C = fms[0].shape[4]
+    lshapes = (ctypes.c_int * 12)(*[int(d) for fm in fms for d in fm.shape[1:4]])
+    ishape = (ctypes.c_float * 3)(*[float(v) for v in VOLUME])
+    fm_ptrs = (vp * 4)(*[fm.data_ptr() for fm in fms])
+    pooled = {c: torch.empty((BATCH, ROIS_PER_IMAGE) + c + (C,), device=dev) for c in CROPS}
+    pgrads = {c: torch.randn((BATCH, ROIS_PER_IMAGE) + c + (C,), device=dev) for c in CROPS}
+    gms = {c: [torch.empty_like(fm) for fm in fms] for c in CROPS}
+    gm_ptrs = {c: (vp * 4)(*[g.data_ptr() for g in gms[c]]) for c in CROPS}
+
+    def fused_step():
+        for c in CROPS:
+            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), ROIS_PER_IMAGE, ishape,
+                                                          c[0], c[1], c[2], ptr(pooled[c]), stream()))
+        for c in CROPS:
+            rb._lib.check(lib.roi3d_pyramid_roi_align_grad(ptr(pgrads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br),
+                                                           ROIS_PER_IMAGE, ishape, c[0], c[1], c[2], stream()))
+
+    for _ in range(3):
+        fused_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fused_step()
+    f1.record()
+    barrier()
+    fused_ms = rb.sharding.max_over_ranks(f0.elapsed_time(f1)) / args.steps
+    fused = {"ms_per_step": round(fused_ms, 4), "value": round(world * total_rois / (fused_ms * 1e-3), 1), "unit": UNIT,
+             "launches_per_step": 4, "note": "roi3d_pyramid_roi_align_fwd/grad: routing + 4 levels + order restore in one "
+             "launch per pool shape (7^3 uses the plane kernel here, the per-op path picks the direct kernel)"}
+    del pooled, pgrads, gms
+
     # ---- NMS3D @6k boxes (cfg1: 6000 -> 1000 @0.7), device resident and host-buffer end to end ----
     nb, ns = roi3d_synth.nms_boxes(6000, VOLUME)
     d_nb, d_ns = torch.from_numpy(nb).to(dev), torch.from_numpy(ns).to(dev)
@@ -253,7 +289,27 @@ def run_ours(args):
     for _ in range(20):
         kept = rb.non_max_suppression_3d(nb, ns, 1000, 0.7)
     nms_e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    # batched: the 8 images of BASELINE cfg4 in one set of launches (ProposalLayer's batch_slice loop, core/models.py:487)
+    nbb = torch.cat([d_nb] * 8)
+    nsb = torch.cat([d_ns] * 8)
+    offs = torch.arange(9, dtype=torch.int32, device=dev) * 6000
+    wsb8 = lib.roi3d_nms3d_batched_workspace_bytes(6000, 8)
+    ws8 = torch.empty(wsb8, dtype=torch.uint8, device=dev)
+    keep8 = torch.empty(8 * 1000, dtype=torch.int32, device=dev)
+    cnt8 = torch.zeros(8, dtype=torch.int32, device=dev)
+    b_ms = []
+    for it in range(30):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rb._lib.check(lib.roi3d_nms3d_batched(ptr(nbb), ptr(nsb), ptr(offs), 8, 6000, 1000, 0.7, ptr(keep8), ptr(cnt8),
+                                              ptr(ws8), wsb8, stream()))
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 5:
+            b_ms.append(a.elapsed_time(b))
+    del ws8
     nms = {"boxes": 6000, "max_out": 1000, "iou_threshold": 0.7, "kept": int(cnt.item()),
+           "batched_8x6000_ms": round(statistics.median(b_ms), 4),
            "ms": round(statistics.median(nms_ms), 4), "ms_p10": round(sorted(nms_ms)[len(nms_ms) // 10], 4),
            "ms_p90": round(sorted(nms_ms)[len(nms_ms) * 9 // 10], 4),
            "boxes_per_s": round(6000 / (statistics.median(nms_ms) * 1e-3)),
@@ -309,6 +365,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "nms3d": nms,
+        "pyramid_fused": fused,
         "ops": per_op,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

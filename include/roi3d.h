@@ -87,6 +87,21 @@ ROI3D_API int roi3d_nms3d(const float *boxes, const float *scores, int n, int ma
                           void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Batched NonMaxSuppression3D: `segments` independent NMS problems in one set of launches.
+ * replaces: the per-image loop of utils.batch_slice around the op (core/utils.py:1459-1544, called from
+ *           ProposalLayer core/models.py:487-490) and the per-class loop of the upstream DetectionLayer design that
+ *           utils.non_max_suppression_3d_graph (core/utils.py:467-503) exists for.
+ * Segment z covers boxes/scores [seg_offsets[z], seg_offsets[z+1]) (device int32 [segments+1], ascending); every
+ * segment has at most n_max boxes.  keep_idx is [segments, max_out] (row z: indices LOCAL to segment z, selection
+ * order), keep_count [segments] (device or pinned host).  Each segment's result is bit-identical to roi3d_nms3d on
+ * that segment alone.  workspace: roi3d_nms3d_batched_workspace_bytes(n_max, segments), 256-byte aligned.
+ * ------------------------------------------------------------------------- */
+ROI3D_API size_t roi3d_nms3d_batched_workspace_bytes(int n_max, int segments);
+ROI3D_API int roi3d_nms3d_batched(const float *boxes, const float *scores, const int *seg_offsets, int segments,
+                                  int n_max, int max_out, float iou_thr, int *keep_idx, int *keep_count,
+                                  void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * CropAndResize3D (forward)
  * replaces: REGISTER_OP("CropAndResize3D") + CropAndResize3DOp::Compute (CAR.so@0x4370);
  *           Python: core/custom_op/custom_op.py:22, called from core/models.py:663-664
@@ -122,6 +137,25 @@ ROI3D_API int roi3d_car3d_grad_boxes(const float *grads, const float *image,
                                      const float *boxes, const int *box_ind, int n,
                                      int ph, int pw, int pd,
                                      float *grad_boxes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused PyramidROIAlign3D (offered IN ADDITION to the drop-in ops)
+ * replaces: PyramidROIAlign.call, core/models.py:604-685 -- box clip + min sizes (:615-632), level routing
+ *           (:637-649), the four per-level crop_and_resize_3d calls (:663-664), the concat / top_k / gather order
+ *           restore (:667-676) and the non-finite scrub (:683) -- by one launch (forward) and four zero-fills plus one
+ *           launch (backward w.r.t. the feature maps; boxes are stop_gradient'ed upstream, :660).
+ * feature_maps / grad_maps: P2..P5, float32 [B, H_l, W_l, D_l, C], level_shapes[l] = {H_l, W_l, D_l};
+ * boxes [B, R, 6] normalized; image_shape = {H, W, D} of the input volume (image_meta); pooled / grads
+ * [B, R, ph, pw, pd, C] in the boxes' own order.  Needs C % 4 == 0 and crop dims <= 64 (ROI3D_EUNSUPPORTED
+ * otherwise: use the per-level ops).  The level index comes from fp32 cbrt/log2 like the TF graph; a ROI whose
+ * level expression falls within an ulp of x.5 may round differently from another libm.
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                          const float *boxes, int rois_per_image, const float image_shape[3],
+                                          int ph, int pw, int pd, float *pooled, roi3d_stream_t stream);
+ROI3D_API int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], const int level_shapes[4][3],
+                                           int B, int C, const float *boxes, int rois_per_image,
+                                           const float image_shape[3], int ph, int pw, int pd, roi3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Tuning / introspection (not part of the reference surface).

@@ -152,3 +152,48 @@ def crop_and_resize_3d_grad_boxes(grads, image, boxes, box_ind):
     _lib().roi3d_oracle_car3d_grad_boxes(_fp(grads), _fp(image), B, H, W, D, C, _fp(boxes), _ip(box_ind), n,
                                          ph, pw, pd, _fp(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# PyramidROIAlign layer (core/models.py:604-685) restated in numpy on top of the op oracle -- checker for the
+# fused kernel.  fp32 arithmetic like the TF graph.
+# ---------------------------------------------------------------------------------------------
+def pyramid_prepare(boxes, image_shape):
+    """Clip to [0,1], min sizes (core/models.py:615-632) and level routing (:637-649). boxes [B,R,6]."""
+    b = np.clip(np.asarray(boxes, np.float32), np.float32(0), np.float32(1)).copy()
+    H, W, D = (np.float32(v) for v in image_shape)
+    eps = np.float32(1e-6)
+    b[..., 3] = np.maximum(b[..., 3], b[..., 0] + eps)
+    b[..., 4] = np.maximum(b[..., 4], b[..., 1] + eps)
+    b[..., 5] = np.maximum(b[..., 5], b[..., 2] + np.float32(1.0) / np.maximum(D, np.float32(1.0)))
+    vol = ((b[..., 3] - b[..., 0]) * (b[..., 4] - b[..., 1]) * (b[..., 5] - b[..., 2])).astype(np.float32)
+    area = np.float32(H * W * D)
+    third = np.float32(1.0 / 3.0)
+    ratio = (np.power(vol, third) / (np.float32(224.0) / np.power(area, third))).astype(np.float32)
+    lvl = (np.log(ratio) / np.log(np.float32(2.0))).astype(np.float32)
+    level = np.minimum(5, np.maximum(2, 4 + np.rint(lvl).astype(np.int32)))
+    return b, level
+
+
+def pyramid_roi_align(boxes, image_shape, feature_maps, pool_shape):
+    """[B,R,ph,pw,pd,C]: per-level CropAndResize3D, original order, non-finite -> 0."""
+    b, level = pyramid_prepare(boxes, image_shape)
+    B, R = b.shape[:2]
+    C = feature_maps[0].shape[4]
+    out = np.zeros((B, R) + tuple(pool_shape) + (C,), np.float32)
+    for i, lv in enumerate(range(2, 6)):
+        ib, ir = np.nonzero(level == lv)
+        if len(ib):
+            out[ib, ir] = crop_and_resize_3d(feature_maps[i], b[ib, ir], ib.astype(np.int32), pool_shape)
+    return np.where(np.isfinite(out), out, np.float32(0))
+
+
+def pyramid_roi_align_grad(grads, boxes, image_shape, level_shapes):
+    """Gradients w.r.t. P2..P5 (list of [B,H_l,W_l,D_l,C])."""
+    b, level = pyramid_prepare(boxes, image_shape)
+    outs = []
+    for i, lv in enumerate(range(2, 6)):
+        ib, ir = np.nonzero(level == lv)
+        outs.append(crop_and_resize_3d_grad_image(np.asarray(grads, np.float32)[ib, ir], b[ib, ir], ib.astype(np.int32),
+                                                  level_shapes[i]))
+    return outs

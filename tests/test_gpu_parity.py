@@ -362,3 +362,91 @@ def test_deferred_host_pipeline(rb, cuda_device):
     for (im, bx, bi, g), out, gi in zip(cases, outs, gis):
         assert np.array_equal(out, oracle.crop_and_resize_3d(im, bx, bi, crop))
         assert rel_ok(gi, oracle.crop_and_resize_3d_grad_image(g, bx, bi, im.shape), BWD_TOL)
+
+
+# =============================================================================================
+# batched / per-class NMS3D
+# =============================================================================================
+def test_nms_batched_matches_per_segment_oracle(rb, cuda_device):
+    rng = np.random.default_rng(21)
+    sizes = [0, 1, 37, 2000, 640, 0, 6000, 33]
+    parts = [roi3d_synth.nms_boxes(max(n, 1), (128, 128, 128), seed=2100 + i) for i, n in enumerate(sizes)]
+    boxes = np.concatenate([p[0][:n] for p, n in zip(parts, sizes)])
+    scores = np.concatenate([p[1][:n] for p, n in zip(parts, sizes)])
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for thr, mo in ((0.7, 1000), (0.3, 50)):
+        got = rb.non_max_suppression_3d_batched(dev(boxes, cuda_device), dev(scores, cuda_device), offs, mo, thr)
+        assert len(got) == len(sizes)
+        for z, n in enumerate(sizes):
+            ref = oracle.non_max_suppression_3d(boxes[offs[z]:offs[z + 1]], scores[offs[z]:offs[z + 1]], mo, thr)
+            assert np.array_equal(got[z].cpu().numpy(), ref), (z, n)
+    # ProposalLayer shape: a batch of images, 6000 boxes each (core/models.py:487-490)
+    B = 4
+    parts = [roi3d_synth.nms_boxes(6000, (128, 128, 128), seed=2200 + i, presorted=True) for i in range(B)]
+    got = rb.non_max_suppression_3d_batched(dev(np.concatenate([p[0] for p in parts]), cuda_device),
+                                            dev(np.concatenate([p[1] for p in parts]), cuda_device),
+                                            np.arange(B + 1) * 6000, 1000, 0.7)
+    for z in range(B):
+        assert np.array_equal(got[z].cpu().numpy(), oracle.non_max_suppression_3d(parts[z][0], parts[z][1], 1000, 0.7))
+
+
+def test_nms_per_class_and_graph_wrapper(rb, cuda_device):
+    """BASELINE cfg3: per-class NMS over 2000 refined boxes; wrapper signature of core/utils.py:467-503."""
+    boxes, scores = roi3d_synth.nms_boxes(2000, (256, 256, 256), seed=23)
+    cls = np.random.default_rng(23).integers(1, 3, 2000)
+    keep, classes = rb.non_max_suppression_3d_per_class(dev(boxes, cuda_device), dev(scores, cuda_device),
+                                                        dev(cls, cuda_device), 100, 0.3)
+    assert classes == [1, 2]
+    for k, c in zip(keep, classes):
+        ix = np.nonzero(cls == c)[0]
+        ref = ix[oracle.non_max_suppression_3d(boxes[ix], scores[ix], 100, 0.3)]
+        assert np.array_equal(k.cpu().numpy(), ref)
+    sel, kidx = rb.non_max_suppression_3d_graph(dev(boxes, cuda_device), dev(scores, cuda_device), 0.3, 200)
+    ref = oracle.non_max_suppression_3d(boxes, scores, 200, 0.3)
+    assert np.array_equal(kidx.cpu().numpy(), ref) and np.array_equal(sel.cpu().numpy(), boxes[ref])
+
+
+# =============================================================================================
+# fused PyramidROIAlign3D (SURVEY.md section 8 row f1)
+# =============================================================================================
+@pytest.mark.parametrize("pool", [(7, 7, 7), (14, 14, 14), (3, 5, 4)])
+def test_fused_pyramid_roi_align(rb, cuda_device, pool):
+    import torch
+    rng = np.random.default_rng(31)
+    B, R, C = 2, 40, 32
+    image_shape = (512, 512, 64)
+    level_hw = [(32, 32), (16, 16), (8, 8), (4, 4)]
+    fms = [rng.standard_normal((B, h, w, 64, C), dtype=np.float32) for h, w in level_hw]
+    boxes = np.stack([roi3d_synth.rois(R, image_shape, seed=3100 + i, side_px=(6.0, 600.0)) for i in range(B)])
+    boxes[0, 0] = 0.0                                           # ProposalLayer zero padding (core/models.py:476-484)
+    boxes[0, 1] = [-0.3, 0.2, 0.1, 0.4, 1.7, 0.9]               # clipped by the layer
+    fms[1][0, 3, 3, 5, 0] = np.inf                              # non-finite features are scrubbed to 0 (:683)
+    _, level = oracle.pyramid_prepare(boxes, image_shape)
+    assert len(np.unique(level)) >= 3                           # several levels exercised
+    t_fms = [dev(f, cuda_device).requires_grad_(True) for f in fms]
+    out = rb.pyramid_roi_align_3d(dev(boxes, cuda_device), image_shape, t_fms, pool)
+    ref = oracle.pyramid_roi_align(boxes, image_shape, fms, pool)
+    assert out.shape == ref.shape
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    grads = rng.standard_normal(ref.shape, dtype=np.float32)
+    out.backward(dev(grads, cuda_device))
+    gref = oracle.pyramid_roi_align_grad(grads, boxes, image_shape, [f.shape for f in fms])
+    for t, g in zip(t_fms, gref):
+        assert rel_ok(t.grad.cpu().numpy(), g, BWD_TOL)
+
+
+def test_fused_pyramid_equals_per_level_ops_cfg2(rb, cuda_device):
+    """cfg2 shapes: the fused launch equals routing on the host + the four drop-in ops, bit for bit."""
+    import torch
+    vol, B, R = (128, 128, 128), 2, 128
+    boxes = np.stack([roi3d_synth.rois(R, vol, seed=2002 * 131 + b) for b in range(B)])
+    torch.manual_seed(5)
+    fms = [torch.randn(roi3d_synth.level_shape(vol, lv, batch=B), device=cuda_device) for lv in roi3d_synth.LEVELS]
+    out = rb.pyramid_roi_align_3d(dev(boxes, cuda_device), vol, fms, (7, 7, 7))
+    bp, level = oracle.pyramid_prepare(boxes, vol)
+    for i, lv in enumerate(roi3d_synth.LEVELS):
+        ib, ir = np.nonzero(level == lv)
+        if len(ib) == 0:
+            continue
+        per = rb.crop_and_resize_3d(fms[i], dev(bp[ib, ir], cuda_device), dev(ib.astype(np.int32), cuda_device), (7, 7, 7))
+        assert torch.equal(out[torch.from_numpy(ib).to(cuda_device), torch.from_numpy(ir).to(cuda_device)], per)
