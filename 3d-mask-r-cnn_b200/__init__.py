@@ -25,6 +25,7 @@ from .custom_op import (        # noqa: E402,F401
     crop_and_resize_3d,
     crop_and_resize_3d_grad_boxes,
     crop_and_resize_3d_grad_image,
+    decode_proposals,
     deferred,
     synchronize,
     get_option,
@@ -33,6 +34,7 @@ from .custom_op import (        # noqa: E402,F401
     non_max_suppression_3d_batched,
     non_max_suppression_3d_graph,
     non_max_suppression_3d_per_class,
+    overlaps_3d,
     pyramid_roi_align_3d,
     reset_kernel_launches,
     set_option,

@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libroi3d_b200.so")
 HEADER = os.path.join(_ROOT, "include", "roi3d.h")
 
-SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_nms.cu"]
+SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_nms.cu", "roi3d_boxes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",      # Blackwell B200 only
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,7 +31,7 @@ EXPORTS = [
     "roi3d_version", "roi3d_strerror", "roi3d_last_cuda_error",
     "roi3d_nms3d_workspace_bytes", "roi3d_nms3d", "roi3d_nms3d_batched_workspace_bytes", "roi3d_nms3d_batched",
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
-    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad",
+    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
     "roi3d_set_option", "roi3d_get_option", "roi3d_kernel_launches", "roi3d_reset_kernel_launches",
 ]
 
@@ -97,6 +97,10 @@ def _declare(lib):
     lib.roi3d_pyramid_roi_align_fwd.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp]
     lib.roi3d_pyramid_roi_align_grad.restype = i
     lib.roi3d_pyramid_roi_align_grad.argtypes = [vp, vp, vp, i, i, vp, i, vp, i, i, i, vp]
+    lib.roi3d_overlaps3d.restype = i
+    lib.roi3d_overlaps3d.argtypes = [vp, i, vp, i, vp, vp]
+    lib.roi3d_decode_proposals.restype = i
+    lib.roi3d_decode_proposals.argtypes = [vp, vp, vp, i, vp, f, vp, vp]
     lib.roi3d_set_option.restype = i
     lib.roi3d_set_option.argtypes = [ctypes.c_char_p, i]
     lib.roi3d_get_option.restype = i

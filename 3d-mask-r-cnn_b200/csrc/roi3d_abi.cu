@@ -147,6 +147,23 @@ int roi3d_car3d_grad_boxes(const float *grads, const float *image, int B, int H,
     return launch_car3d_grad_boxes(grads, image, boxes, box_ind, g, grad_boxes, static_cast<cudaStream_t>(stream));
 }
 
+int roi3d_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *overlaps, roi3d_stream_t stream)
+{
+    if (n < 0 || m < 0) return ROI3D_EINVAL;
+    if (n == 0 || m == 0) return ROI3D_OK;
+    if (!boxes1 || !boxes2 || !overlaps) return ROI3D_EINVAL;
+    return launch_overlaps3d(boxes1, n, boxes2, m, overlaps, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_decode_proposals(const float *anchors, const float *deltas, const int *index, int n, const float std_dev[6],
+                           float image_depth, float *boxes, roi3d_stream_t stream)
+{
+    if (n < 0 || !std_dev) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!anchors || !deltas || !boxes) return ROI3D_EINVAL;
+    return launch_decode_proposals(anchors, deltas, index, n, std_dev, image_depth, boxes, static_cast<cudaStream_t>(stream));
+}
+
 static int pyramid_check(const int level_shapes[4][3], int B, int C, const float *boxes, int rois_per_image,
                          const float image_shape[3], int ph, int pw, int pd)
 {

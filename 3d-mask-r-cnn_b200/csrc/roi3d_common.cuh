@@ -126,6 +126,9 @@ int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W
 int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],
                         int B, int C, const float *boxes, int rois_per_image, float imH, float imW, float imD,
                         int ph, int pw, int pd, cudaStream_t stream);
+int launch_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *out, cudaStream_t stream);
+int launch_decode_proposals(const float *anchors, const float *deltas, const int *index, int n, const float std_dev[6],
+                            float image_depth, float *boxes, cudaStream_t stream);
 size_t nms3d_workspace_bytes(int n, int segments);
 int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n, int max_out,
                  float thr, int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);

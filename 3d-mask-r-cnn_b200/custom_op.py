@@ -34,7 +34,7 @@ __all__ = [
     "InvalidArgumentError", "crop_and_resize_3d", "crop_and_resize_3d_grad_image",
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
     "non_max_suppression_3d_batched", "non_max_suppression_3d_per_class", "non_max_suppression_3d_graph",
-    "pyramid_roi_align_3d", "PyramidROIAlign3DFunction",
+    "pyramid_roi_align_3d", "PyramidROIAlign3DFunction", "overlaps_3d", "decode_proposals",
     "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize",
 ]
 
@@ -496,6 +496,35 @@ def pyramid_roi_align_3d(boxes, image_shape, feature_maps, pool_shape):
     _require(all(fm.dim() == 5 and fm.shape[0] == boxes.shape[0] for fm in feature_maps), "feature maps must be [B,H,W,D,C]")
     del dev
     return PyramidROIAlign3DFunction.apply(boxes, tuple(image_shape), tuple(int(v) for v in pool_shape), *feature_maps)
+
+
+# ---------------------------------------------------------------------------------------
+# box-space helpers
+# ---------------------------------------------------------------------------------------
+def overlaps_3d(boxes1, boxes2):
+    """``overlaps_graph`` (core/models.py:695-733): IoU matrix ``[N, M]`` float32 of two CUDA box sets."""
+    dev = _device()
+    b1, b2 = _Arg(boxes1, torch.float32, dev), _Arg(boxes2, torch.float32, dev)
+    _require(b1.dev.dim() == 2 and b1.dev.shape[1] == 6 and b2.dev.dim() == 2 and b2.dev.shape[1] == 6, "boxes must be [N, 6]")
+    n, m = b1.dev.shape[0], b2.dev.shape[0]
+    out = torch.empty((n, m), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().roi3d_overlaps3d(_ptr(b1.dev), n, _ptr(b2.dev), m, _ptr(out), _stream_ptr()))
+    return _finish(out, b1.host or b2.host, b1.numpy)
+
+
+def decode_proposals(anchors, deltas, std_dev, image_depth, index=None):
+    """ProposalLayer's box front-end (core/models.py:397-447): ``deltas * std_dev`` -> clip +-3 ->
+    ``apply_box_deltas_graph`` -> clip to [0,1] -> min sizes.  ``index`` (the ``tf.nn.top_k`` indices) gathers rows."""
+    dev = _device()
+    a, d = _Arg(anchors, torch.float32, dev), _Arg(deltas, torch.float32, dev)
+    _require(a.dev.dim() == 2 and a.dev.shape[1] == 6 and tuple(d.dev.shape) == tuple(a.dev.shape), "anchors / deltas must be [N, 6]")
+    ix = _Arg(index, torch.int32, dev).dev if index is not None else None
+    n = int(ix.shape[0]) if ix is not None else int(a.dev.shape[0])
+    out = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    std = (ctypes.c_float * 6)(*[float(v) for v in std_dev])
+    _lib.check(_lib.load().roi3d_decode_proposals(_ptr(a.dev), _ptr(d.dev), _ptr(ix) if ix is not None else None, n, std,
+                                                  float(image_depth), _ptr(out), _stream_ptr()))
+    return _finish(out, a.host or d.host, a.numpy)
 
 
 # ---------------------------------------------------------------------------------------

@@ -158,6 +158,19 @@ ROI3D_API int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad
                                            const float image_shape[3], int ph, int pw, int pd, roi3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Box-space helpers either side of the ops
+ * roi3d_overlaps3d        replaces overlaps_graph, core/models.py:695-733: overlaps [n,m] float32, fp32 arithmetic of
+ *                         the TF graph (union clamped with 1e-10; NOT the NMS op's IOU<float>).
+ * roi3d_decode_proposals  replaces ProposalLayer's per-anchor chain between top_k and NMS, core/models.py:397-447:
+ *                         deltas * std_dev, clip +-3, apply_box_deltas_graph (:280-337), clip to [0,1], min sizes.
+ *                         index (int32 [n], may be NULL) gathers anchors/deltas rows first (the top_k indices).
+ * ------------------------------------------------------------------------- */
+ROI3D_API int roi3d_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *overlaps,
+                               roi3d_stream_t stream);
+ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, const int *index, int n,
+                                     const float std_dev[6], float image_depth, float *boxes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Tuning / introspection (not part of the reference surface).
  * roi3d_set_option: process-wide knobs used by the benchmarks and tests to
  * select a kernel variant; the defaults are the production choice.

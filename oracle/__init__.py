@@ -197,3 +197,43 @@ def pyramid_roi_align_grad(grads, boxes, image_shape, level_shapes):
         outs.append(crop_and_resize_3d_grad_image(np.asarray(grads, np.float32)[ib, ir], b[ib, ir], ib.astype(np.int32),
                                                   level_shapes[i]))
     return outs
+
+
+# ---------------------------------------------------------------------------------------------
+# box-space helpers: numpy restatements of the TF graph code, fp32
+# ---------------------------------------------------------------------------------------------
+def overlaps_graph(boxes1, boxes2):
+    """core/models.py:695-733."""
+    b1 = np.asarray(boxes1, np.float32)[:, None, :]
+    b2 = np.asarray(boxes2, np.float32)[None, :, :]
+    z = np.float32(0)
+    y1 = np.maximum(b1[..., 0], b2[..., 0]); x1 = np.maximum(b1[..., 1], b2[..., 1]); z1 = np.maximum(b1[..., 2], b2[..., 2])
+    y2 = np.minimum(b1[..., 3], b2[..., 3]); x2 = np.minimum(b1[..., 4], b2[..., 4]); z2 = np.minimum(b1[..., 5], b2[..., 5])
+    inter = np.maximum(y2 - y1, z) * np.maximum(x2 - x1, z) * np.maximum(z2 - z1, z)
+    v1 = (b1[..., 3] - b1[..., 0]) * (b1[..., 4] - b1[..., 1]) * (b1[..., 5] - b1[..., 2])
+    v2 = (b2[..., 3] - b2[..., 0]) * (b2[..., 4] - b2[..., 1]) * (b2[..., 5] - b2[..., 2])
+    union = v1 + v2 - inter
+    return (inter / np.maximum(union, np.float32(1e-10))).astype(np.float32)
+
+
+def decode_proposals(anchors, deltas, std_dev, image_depth, index=None):
+    """core/models.py:397-447 with apply_box_deltas_graph (:280-337) and clip_boxes_graph (:340-364)."""
+    a = np.asarray(anchors, np.float32)
+    d = np.asarray(deltas, np.float32) * np.asarray(std_dev, np.float32)[None, :]
+    d = np.clip(d, np.float32(-3), np.float32(3))
+    if index is not None:
+        a, d = a[index], d[index]
+    half = np.float32(0.5)
+    h = a[:, 3] - a[:, 0]; w = a[:, 4] - a[:, 1]; dp = a[:, 5] - a[:, 2]
+    cy = a[:, 0] + half * h; cx = a[:, 1] + half * w; cz = a[:, 2] + half * dp
+    cy = cy + d[:, 0] * h; cx = cx + d[:, 1] * w; cz = cz + d[:, 2] * dp
+    h = h * np.exp(d[:, 3]); w = w * np.exp(d[:, 4]); dp = dp * np.exp(d[:, 5])
+    y1 = cy - half * h; x1 = cx - half * w; z1 = cz - half * dp
+    out = np.stack([y1, x1, z1, y1 + h, x1 + w, z1 + dp], axis=1).astype(np.float32)
+    out = np.clip(out, np.float32(0), np.float32(1))
+    depth = np.float32(max(float(image_depth), 1.0))
+    min_dz = np.maximum(np.float32(1.0) / depth, np.float32(1e-4))
+    out[:, 3] = np.maximum(out[:, 3], out[:, 0] + np.float32(1e-6))
+    out[:, 4] = np.maximum(out[:, 4], out[:, 1] + np.float32(1e-6))
+    out[:, 5] = np.maximum(out[:, 5], out[:, 2] + min_dz)
+    return out

@@ -450,3 +450,33 @@ def test_fused_pyramid_equals_per_level_ops_cfg2(rb, cuda_device):
             continue
         per = rb.crop_and_resize_3d(fms[i], dev(bp[ib, ir], cuda_device), dev(ib.astype(np.int32), cuda_device), (7, 7, 7))
         assert torch.equal(out[torch.from_numpy(ib).to(cuda_device), torch.from_numpy(ir).to(cuda_device)], per)
+
+
+# =============================================================================================
+# box-space helpers
+# =============================================================================================
+def test_overlaps_graph_bit_exact(rb, cuda_device):
+    b1 = roi3d_synth.rois(700, (128, 128, 128), seed=41, side_px=(8, 64))
+    b2 = roi3d_synth.rois(37, (128, 128, 128), seed=42, side_px=(8, 64))
+    b2[:20] = b1[:20] + np.float32(0.01)                        # real overlaps
+    b1[5] = b1[5][[3, 4, 5, 0, 1, 2]]                           # negative volume: overlaps_graph does not reorder corners
+    out = rb.overlaps_3d(dev(b1, cuda_device), dev(b2, cuda_device)).cpu().numpy()
+    ref = oracle.overlaps_graph(b1, b2)
+    assert out.shape == (700, 37) and (ref > 0).sum() > 20
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_decode_proposals_matches_graph(rb, cuda_device):
+    rng = np.random.default_rng(43)
+    n = 20000
+    anchors = roi3d_synth.rois(n, (128, 128, 128), seed=44, side_px=(4, 96))
+    deltas = (rng.standard_normal((n, 6)) * 3).astype(np.float32)
+    std = (0.1, 0.1, 0.1, 0.2, 0.2, 0.2)
+    index = rng.permutation(n)[:6000].astype(np.int32)
+    for ix in (None, index):
+        out = rb.decode_proposals(dev(anchors, cuda_device), dev(deltas, cuda_device), std, 128,
+                                  None if ix is None else dev(ix, cuda_device)).cpu().numpy()
+        ref = oracle.decode_proposals(anchors, deltas, std, 128, ix)
+        assert out.shape == ref.shape
+        assert np.allclose(out, ref, rtol=2e-6, atol=2e-7)      # expf vs numpy exp: <= 2 ulp, then clipped to [0,1]
+        assert (out[:, 3:] > out[:, :3]).all() and out.min() >= 0 and out.max() <= 1 + 1.0 / 128 + 1e-6   # min-size may exceed 1
