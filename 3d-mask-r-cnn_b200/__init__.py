@@ -35,6 +35,8 @@ from .custom_op import (        # noqa: E402,F401
     non_max_suppression_3d_graph,
     non_max_suppression_3d_per_class,
     overlaps_3d,
+    proposal_layer,
+    top_k_set,
     pyramid_roi_align_3d,
     reset_kernel_launches,
     set_option,

@@ -32,6 +32,7 @@ EXPORTS = [
     "roi3d_nms3d_workspace_bytes", "roi3d_nms3d", "roi3d_nms3d_batched_workspace_bytes", "roi3d_nms3d_batched",
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
     "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
+    "roi3d_topk_workspace_bytes", "roi3d_topk", "roi3d_gather_pad_boxes",
     "roi3d_set_option", "roi3d_get_option", "roi3d_kernel_launches", "roi3d_reset_kernel_launches",
 ]
 
@@ -101,6 +102,12 @@ def _declare(lib):
     lib.roi3d_overlaps3d.argtypes = [vp, i, vp, i, vp, vp]
     lib.roi3d_decode_proposals.restype = i
     lib.roi3d_decode_proposals.argtypes = [vp, vp, vp, i, vp, f, vp, vp]
+    lib.roi3d_topk_workspace_bytes.restype = sz
+    lib.roi3d_topk_workspace_bytes.argtypes = [i]
+    lib.roi3d_topk.restype = i
+    lib.roi3d_topk.argtypes = [vp, i, i, vp, vp, vp, sz, vp]
+    lib.roi3d_gather_pad_boxes.restype = i
+    lib.roi3d_gather_pad_boxes.argtypes = [vp, vp, vp, i, vp, vp]
     lib.roi3d_set_option.restype = i
     lib.roi3d_set_option.argtypes = [ctypes.c_char_p, i]
     lib.roi3d_get_option.restype = i

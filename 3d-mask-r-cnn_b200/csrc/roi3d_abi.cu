@@ -164,6 +164,26 @@ int roi3d_decode_proposals(const float *anchors, const float *deltas, const int 
     return launch_decode_proposals(anchors, deltas, index, n, std_dev, image_depth, boxes, static_cast<cudaStream_t>(stream));
 }
 
+size_t roi3d_topk_workspace_bytes(int n) { return topk_workspace_bytes(n > 0 ? n : 1); }
+
+int roi3d_topk(const float *scores, int n, int k, int *idx_out, float *scores_out, void *workspace, size_t workspace_bytes,
+               roi3d_stream_t stream)
+{
+    if (n < 0 || k < 0 || k > n) return ROI3D_EINVAL;
+    if (k == 0) return ROI3D_OK;
+    if (!scores || !idx_out) return ROI3D_EINVAL;
+    return launch_topk(scores, n, k, idx_out, scores_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_gather_pad_boxes(const float *boxes, const int *keep_idx, const int *keep_count, int proposal_count,
+                           float *proposals, roi3d_stream_t stream)
+{
+    if (proposal_count < 0) return ROI3D_EINVAL;
+    if (proposal_count == 0) return ROI3D_OK;
+    if (!boxes || !keep_idx || !keep_count || !proposals) return ROI3D_EINVAL;
+    return launch_gather_pad_boxes(boxes, keep_idx, keep_count, proposal_count, proposals, static_cast<cudaStream_t>(stream));
+}
+
 static int pyramid_check(const int level_shapes[4][3], int B, int C, const float *boxes, int rois_per_image,
                          const float image_shape[3], int ph, int pw, int pd)
 {

@@ -104,3 +104,246 @@ int launch_decode_proposals(const float *anchors, const float *deltas, const int
 }
 
 }  // namespace roi3d
+
+// =====================================================================================================
+// top-k selection (tf.nn.top_k(scores, k), core/models.py:403-404) as a 3-pass radix select on the 32-bit
+// descending-order key, followed by an index-ordered compaction.  The selected SET is exactly TF's (ties at the
+// threshold broken towards lower indices); it is emitted in ascending index order, which is all the NMS that follows
+// needs (it sorts by (score, position) itself, so position ties resolve like top_k's "lower index first").
+// =====================================================================================================
+namespace roi3d {
+
+__device__ __forceinline__ unsigned topk_key(float s) {
+    // ascending unsigned key <=> descending float; -0 == +0; NaN sorts last
+    if (s != s) return 0xFFFFFFFFu;
+    if (s == 0.0f) s = 0.0f;
+    const unsigned b = __float_as_uint(s);
+    const unsigned asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~asc;
+}
+
+struct TopkState {                  // lives in the workspace
+    unsigned prefix;                // key bits decided so far (high bits)
+    unsigned need;                  // how many elements still to take among the current prefix class
+    unsigned hist[2048];
+};
+
+constexpr int TK_THREADS = 1024;
+
+// pass p in {0,1,2}: bits [31:21], [20:10], [9:0]
+__device__ __forceinline__ int tk_shift(int p) { return p == 0 ? 21 : (p == 1 ? 10 : 0); }
+__device__ __forceinline__ int tk_bits(int p) { return p == 2 ? 10 : 11; }
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_hist_kernel(const float *__restrict__ scores, int n, int pass, TopkState *__restrict__ st)
+{
+    __shared__ unsigned s_hist[2048];
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    const int shift = tk_shift(pass), nb = tk_bits(pass);
+    const unsigned prefix = st->prefix;
+    const int pshift = shift + nb;                               // bits above the current digit
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned k = topk_key(__ldg(scores + i));
+        if (pass == 0 || (k >> pshift) == (prefix >> pshift))
+            atomicAdd(&s_hist[(k >> shift) & ((1u << nb) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x)
+        if (s_hist[t]) atomicAdd(&st->hist[t], s_hist[t]);
+}
+
+// one CTA: find the digit where the running count (best keys first) reaches `need`; clear the histogram
+__global__ void __launch_bounds__(TK_THREADS)
+topk_pick_kernel(int pass, int k_total, TopkState *__restrict__ st)
+{
+    __shared__ unsigned s_cnt[2048];
+    __shared__ unsigned s_sum[TK_THREADS];
+    const int nb = tk_bits(pass), bins = 1 << nb, shift = tk_shift(pass);
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) { s_cnt[t] = st->hist[t]; st->hist[t] = 0; }
+    __syncthreads();
+    // inclusive scan of 2 bins per thread
+    const unsigned a = (2 * threadIdx.x < bins) ? s_cnt[2 * threadIdx.x] : 0u;
+    const unsigned b = (2 * threadIdx.x + 1 < bins) ? s_cnt[2 * threadIdx.x + 1] : 0u;
+    s_sum[threadIdx.x] = a + b;
+    __syncthreads();
+    for (int o = 1; o < TK_THREADS; o <<= 1) {
+        const unsigned v = (threadIdx.x >= o) ? s_sum[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned need = (pass == 0) ? (unsigned)k_total : st->need;
+    const unsigned before = s_sum[threadIdx.x] - (a + b);        // count of strictly better digits
+    __syncthreads();
+    // the digit d with before(d) < need <= before(d) + cnt(d)
+    if (a && before < need && need <= before + a) {
+        st->prefix = (pass == 0 ? 0u : st->prefix) | ((unsigned)(2 * threadIdx.x) << shift);
+        st->need = need - before;
+    } else if (b && before + a < need && need <= before + a + b) {
+        st->prefix = (pass == 0 ? 0u : st->prefix) | ((unsigned)(2 * threadIdx.x + 1) << shift);
+        st->need = need - (before + a);
+    }
+}
+
+// per-range counts of keys strictly better than / equal to the threshold key
+__global__ void __launch_bounds__(TK_THREADS)
+topk_count_kernel(const float *__restrict__ scores, int n, int range, const TopkState *__restrict__ st,
+                  unsigned *__restrict__ less_cnt, unsigned *__restrict__ eq_cnt)
+{
+    __shared__ unsigned s_less, s_eq;
+    if (threadIdx.x == 0) { s_less = 0; s_eq = 0; }
+    __syncthreads();
+    const unsigned T = st->prefix;
+    const int i0 = blockIdx.x * range, i1 = min(n, i0 + range);
+    unsigned l = 0, e = 0;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const unsigned k = topk_key(__ldg(scores + i));
+        l += k < T;
+        e += k == T;
+    }
+    for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+    if ((threadIdx.x & 31) == 0) { if (l) atomicAdd(&s_less, l); if (e) atomicAdd(&s_eq, e); }
+    __syncthreads();
+    if (threadIdx.x == 0) { less_cnt[blockIdx.x] = s_less; eq_cnt[blockIdx.x] = s_eq; }
+}
+
+// one CTA: exclusive scans over the ranges -> eq_off[b] (rank of the range's first equal key) and sel_off[b]
+__global__ void __launch_bounds__(TK_THREADS)
+topk_scan_kernel(int nblocks, const TopkState *__restrict__ st, const unsigned *__restrict__ less_cnt,
+                 const unsigned *__restrict__ eq_cnt, unsigned *__restrict__ eq_off, unsigned *__restrict__ sel_off)
+{
+    __shared__ unsigned s_a[TK_THREADS];
+    const unsigned need_eq = st->need;
+    const int t = threadIdx.x;
+    const unsigned e = t < nblocks ? eq_cnt[t] : 0u, l = t < nblocks ? less_cnt[t] : 0u;
+    s_a[t] = e;
+    __syncthreads();
+    for (int o = 1; o < TK_THREADS; o <<= 1) {
+        const unsigned v = (t >= o) ? s_a[t - o] : 0u;
+        __syncthreads();
+        s_a[t] += v;
+        __syncthreads();
+    }
+    const unsigned eoff = s_a[t] - e;
+    const unsigned take = eoff >= need_eq ? 0u : min(e, need_eq - eoff);
+    __syncthreads();
+    s_a[t] = l + take;
+    __syncthreads();
+    for (int o = 1; o < TK_THREADS; o <<= 1) {
+        const unsigned v = (t >= o) ? s_a[t - o] : 0u;
+        __syncthreads();
+        s_a[t] += v;
+        __syncthreads();
+    }
+    if (t < nblocks) { eq_off[t] = eoff; sel_off[t] = s_a[t] - (l + take); }
+}
+
+// index-ordered compaction of the selected set
+__global__ void __launch_bounds__(TK_THREADS)
+topk_compact_kernel(const float *__restrict__ scores, int n, int range, const TopkState *__restrict__ st,
+                    const unsigned *__restrict__ eq_off, const unsigned *__restrict__ sel_off,
+                    int *__restrict__ idx_out, float *__restrict__ scores_out)
+{
+    __shared__ unsigned s_warp[2][32];
+    __shared__ unsigned s_base[2];
+    const unsigned T = st->prefix, need_eq = st->need;
+    const int i0 = blockIdx.x * range, i1 = min(n, i0 + range);
+    if (threadIdx.x == 0) { s_base[0] = eq_off[blockIdx.x]; s_base[1] = sel_off[blockIdx.x]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c0 = i0; c0 < i1; c0 += TK_THREADS) {
+        const int i = c0 + threadIdx.x;
+        float s = 0.f;
+        unsigned k = 0xFFFFFFFFu;
+        const bool in = i < i1;
+        if (in) { s = __ldg(scores + i); k = topk_key(s); }
+        const bool eq = in && k == T, less = in && k < T;
+        // rank among the equal keys of this chunk
+        const unsigned eb = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_warp[0][warp] = __popc(eb);
+        __syncthreads();
+        unsigned ebefore = 0;
+        for (int w = 0; w < warp; ++w) ebefore += s_warp[0][w];
+        const unsigned erank = s_base[0] + ebefore + __popc(eb & ((1u << lane) - 1u));
+        const bool sel = less || (eq && erank < need_eq);
+        const unsigned sb = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) s_warp[1][warp] = __popc(sb);
+        __syncthreads();
+        unsigned sbefore = 0, etotal = 0, stotal = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (w < warp) sbefore += s_warp[1][w];
+            etotal += s_warp[0][w];
+            stotal += s_warp[1][w];
+        }
+        if (sel) {
+            const unsigned pos = s_base[1] + sbefore + __popc(sb & ((1u << lane) - 1u));
+            idx_out[pos] = i;
+            if (scores_out) scores_out[pos] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_base[0] += etotal; s_base[1] += stotal; }
+        __syncthreads();
+    }
+}
+
+// proposals[P,6] = boxes[keep[0..count)] zero-padded (ProposalLayer, core/models.py:476-484); count read on device
+__global__ void __launch_bounds__(256)
+gather_pad_boxes_kernel(const float *__restrict__ boxes, const int *__restrict__ keep, const int *__restrict__ count,
+                        int p, float *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p * 6) return;
+    const int r = t / 6, c = t - r * 6;
+    out[t] = (r < *count) ? __ldg(boxes + (size_t)__ldg(keep + r) * 6 + c) : 0.0f;
+}
+
+static int topk_range(int n) {
+    int range = 4096;
+    while ((long long)range * TK_THREADS < n) range *= 2;       // at most 1024 ranges (single-CTA scan)
+    return range;
+}
+
+size_t topk_workspace_bytes(int n) {
+    const int nblocks = (n + topk_range(n) - 1) / topk_range(n);
+    return 256 * ((sizeof(TopkState) + 255) / 256) + 4 * 256 * ((sizeof(unsigned) * (size_t)(nblocks > 0 ? nblocks : 1) + 255) / 256);
+}
+
+int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_out, void *ws, size_t ws_bytes,
+                cudaStream_t stream)
+{
+    if (ws == nullptr || ws_bytes < topk_workspace_bytes(n) || (reinterpret_cast<uintptr_t>(ws) & 255)) return ROI3D_EWORKSPACE;
+    const int range = topk_range(n), nblocks = (n + range - 1) / range;
+    char *base = static_cast<char *>(ws);
+    TopkState *st = reinterpret_cast<TopkState *>(base);
+    const size_t st_bytes = 256 * ((sizeof(TopkState) + 255) / 256);
+    const size_t arr = 256 * ((sizeof(unsigned) * (size_t)nblocks + 255) / 256);
+    unsigned *less_cnt = reinterpret_cast<unsigned *>(base + st_bytes);
+    unsigned *eq_cnt = reinterpret_cast<unsigned *>(base + st_bytes + arr);
+    unsigned *eq_off = reinterpret_cast<unsigned *>(base + st_bytes + 2 * arr);
+    unsigned *sel_off = reinterpret_cast<unsigned *>(base + st_bytes + 3 * arr);
+    ROI3D_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(TopkState), stream));
+    const int hgrid = min((n + TK_THREADS - 1) / TK_THREADS, kNumSMs * 2);
+    for (int pass = 0; pass < 3; ++pass) {
+        topk_hist_kernel<<<hgrid, TK_THREADS, 0, stream>>>(scores, n, pass, st);
+        ROI3D_LAUNCH_CHECK();
+        topk_pick_kernel<<<1, TK_THREADS, 0, stream>>>(pass, k, st);
+        ROI3D_LAUNCH_CHECK();
+    }
+    topk_count_kernel<<<nblocks, TK_THREADS, 0, stream>>>(scores, n, range, st, less_cnt, eq_cnt);
+    ROI3D_LAUNCH_CHECK();
+    topk_scan_kernel<<<1, TK_THREADS, 0, stream>>>(nblocks, st, less_cnt, eq_cnt, eq_off, sel_off);
+    ROI3D_LAUNCH_CHECK();
+    topk_compact_kernel<<<nblocks, TK_THREADS, 0, stream>>>(scores, n, range, st, eq_off, sel_off, idx_out, scores_out);
+    ROI3D_LAUNCH_CHECK();
+    return ROI3D_OK;
+}
+
+int launch_gather_pad_boxes(const float *boxes, const int *keep, const int *count, int p, float *out, cudaStream_t stream)
+{
+    gather_pad_boxes_kernel<<<(p * 6 + 255) / 256, 256, 0, stream>>>(boxes, keep, count, p, out);
+    ROI3D_LAUNCH_CHECK();
+    return ROI3D_OK;
+}
+
+}  // namespace roi3d

@@ -129,6 +129,10 @@ int launch_pyramid_grad(const float *grads, float *const grad_images[4], const i
 int launch_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *out, cudaStream_t stream);
 int launch_decode_proposals(const float *anchors, const float *deltas, const int *index, int n, const float std_dev[6],
                             float image_depth, float *boxes, cudaStream_t stream);
+size_t topk_workspace_bytes(int n);
+int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_out, void *ws, size_t ws_bytes,
+                cudaStream_t stream);
+int launch_gather_pad_boxes(const float *boxes, const int *keep, const int *count, int p, float *out, cudaStream_t stream);
 size_t nms3d_workspace_bytes(int n, int segments);
 int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n, int max_out,
                  float thr, int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);

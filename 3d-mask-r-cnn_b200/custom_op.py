@@ -34,7 +34,7 @@ __all__ = [
     "InvalidArgumentError", "crop_and_resize_3d", "crop_and_resize_3d_grad_image",
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
     "non_max_suppression_3d_batched", "non_max_suppression_3d_per_class", "non_max_suppression_3d_graph",
-    "pyramid_roi_align_3d", "PyramidROIAlign3DFunction", "overlaps_3d", "decode_proposals",
+    "pyramid_roi_align_3d", "PyramidROIAlign3DFunction", "overlaps_3d", "decode_proposals", "top_k_set", "proposal_layer",
     "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize",
 ]
 
@@ -525,6 +525,53 @@ def decode_proposals(anchors, deltas, std_dev, image_depth, index=None):
     _lib.check(_lib.load().roi3d_decode_proposals(_ptr(a.dev), _ptr(d.dev), _ptr(ix) if ix is not None else None, n, std,
                                                   float(image_depth), _ptr(out), _stream_ptr()))
     return _finish(out, a.host or d.host, a.numpy)
+
+
+def top_k_set(scores, k):
+    """The index SET of ``tf.nn.top_k(scores, k)`` (threshold ties -> lower indices), in ascending index order, and
+    the matching scores -- device radix select, no host sync.  CUDA float32 ``scores [N]`` only."""
+    dev = _device()
+    s = _Arg(scores, torch.float32, dev)
+    _require(s.dev.dim() == 1, "scores must be 1-D")
+    n, k = int(s.dev.shape[0]), int(k)
+    _require(0 <= k <= n, "k must be in [0, N]")
+    idx = torch.empty(k, dtype=torch.int32, device=dev)
+    val = torch.empty(k, dtype=torch.float32, device=dev)
+    if k:
+        lib = _lib.load()
+        ws = _workspace(lib.roi3d_topk_workspace_bytes(n), dev)
+        _lib.check(lib.roi3d_topk(_ptr(s.dev), n, k, _ptr(idx), _ptr(val), _ptr(ws), ws.numel(), _stream_ptr()))
+    return idx, val
+
+
+def proposal_layer(scores, deltas, anchors, std_dev, image_depth, pre_nms_limit, proposal_count, nms_threshold):
+    """One image of ``ProposalLayer.call`` (core/models.py:382-500) entirely on the device and without a host
+    synchronisation: top-k -> delta decode + clip + min sizes -> NMS3D -> gather -> zero-pad to ``proposal_count``.
+
+    ``scores [N]`` (foreground probabilities), ``deltas [N,6]``, ``anchors [N,6]`` CUDA float32.  Returns
+    ``proposals [proposal_count, 6]`` and the device int32 count of real proposals."""
+    dev = _device()
+    sc, dl, an = _Arg(scores, torch.float32, dev), _Arg(deltas, torch.float32, dev), _Arg(anchors, torch.float32, dev)
+    n = int(sc.dev.shape[0])
+    k = min(int(pre_nms_limit), n)
+    P = int(proposal_count)
+    lib = _lib.load()
+    out = torch.empty((P, 6), dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    if k == 0 or P == 0:
+        return out.zero_(), count
+    idx, val = top_k_set(sc.dev, k)
+    boxes = torch.empty((k, 6), dtype=torch.float32, device=dev)
+    std = (ctypes.c_float * 6)(*[float(v) for v in std_dev])
+    _lib.check(lib.roi3d_decode_proposals(_ptr(an.dev), _ptr(dl.dev), _ptr(idx), k, std, float(image_depth), _ptr(boxes),
+                                          _stream_ptr()))
+    keep = torch.empty(P, dtype=torch.int32, device=dev)
+    nbytes = lib.roi3d_nms3d_workspace_bytes(k)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)        # separate from top_k_set's cached workspace
+    _lib.check(lib.roi3d_nms3d(_ptr(boxes), _ptr(val), k, P, float(nms_threshold), _ptr(keep), _ptr(count), _ptr(ws),
+                               ws.numel(), _stream_ptr()))
+    _lib.check(lib.roi3d_gather_pad_boxes(_ptr(boxes), _ptr(keep), _ptr(count), P, _ptr(out), _stream_ptr()))
+    return out, count
 
 
 # ---------------------------------------------------------------------------------------

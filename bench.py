@@ -315,6 +315,25 @@ def run_ours(args):
            "boxes_per_s": round(6000 / (statistics.median(nms_ms) * 1e-3)),
            "e2e_host_buffers_ms": round(nms_e2e_ms, 4), "e2e_kept": int(len(kept))}
 
+    # ---- ProposalLayer on the device (cfg1 front half): top-k 6000 of N anchors -> decode -> NMS3D -> pad ----
+    n_anchor = 393216                                   # 32*32*128*3 anchors of the finest RPN level at 128^3
+    an = torch.from_numpy(roi3d_synth.nms_boxes(n_anchor, VOLUME, seed=77)[0]).to(dev)
+    torch.manual_seed(78)
+    dlt = torch.randn((n_anchor, 6), device=dev) * 0.5
+    scr = torch.rand(n_anchor, device=dev)
+    pl_ms = []
+    for it in range(25):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        props, pcount = rb.proposal_layer(scr, dlt, an, (0.1, 0.1, 0.1, 0.2, 0.2, 0.2), VOLUME[2], 6000, 1000, 0.7)
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 5:
+            pl_ms.append(a.elapsed_time(b))
+    proposal = {"anchors": n_anchor, "pre_nms_limit": 6000, "proposal_count": 1000, "kept": int(pcount.item()),
+                "ms": round(statistics.median(pl_ms), 4), "note": "top-k radix select + decode + NMS3D + gather/pad, no host sync"}
+    del an, dlt, scr
+
     # ---- end to end through the public API with host buffers ---------------------------------------
     # Per step: every level's feature map is uploaded once (pinned host -> device), boxes / box indices / grads
     # go in as host buffers with each call, every crop and every grad image comes back to pinned host memory.
@@ -366,6 +385,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "nms3d": nms,
         "pyramid_fused": fused,
+        "proposal_layer": proposal,
         "ops": per_op,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

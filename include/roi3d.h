@@ -167,6 +167,17 @@ ROI3D_API int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad
  * ------------------------------------------------------------------------- */
 ROI3D_API int roi3d_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *overlaps,
                                roi3d_stream_t stream);
+/* roi3d_topk              replaces tf.nn.top_k(scores, k) ahead of NMS (core/models.py:403-404): the selected SET equals
+ *                         TF's (threshold ties -> lower indices); idx_out [k] is in ASCENDING INDEX order (the NMS that
+ *                         follows orders by (score, position) itself, so ties resolve as with top_k's sorted output);
+ *                         scores_out [k] optional.  3-pass radix select + ordered compaction, 9 launches, no host sync.
+ * roi3d_gather_pad_boxes  replaces tf.gather(boxes, idx) + tf.pad to proposal_count (core/models.py:476-484); the keep
+ *                         count is read on the device, so ProposalLayer needs no host synchronisation at all. */
+ROI3D_API size_t roi3d_topk_workspace_bytes(int n);
+ROI3D_API int roi3d_topk(const float *scores, int n, int k, int *idx_out, float *scores_out,
+                         void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
+ROI3D_API int roi3d_gather_pad_boxes(const float *boxes, const int *keep_idx, const int *keep_count, int proposal_count,
+                                     float *proposals, roi3d_stream_t stream);
 ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, const int *index, int n,
                                      const float std_dev[6], float image_depth, float *boxes, roi3d_stream_t stream);
 

@@ -480,3 +480,48 @@ def test_decode_proposals_matches_graph(rb, cuda_device):
         assert out.shape == ref.shape
         assert np.allclose(out, ref, rtol=2e-6, atol=2e-7)      # expf vs numpy exp: <= 2 ulp, then clipped to [0,1]
         assert (out[:, 3:] > out[:, :3]).all() and out.min() >= 0 and out.max() <= 1 + 1.0 / 128 + 1e-6   # min-size may exceed 1
+
+
+def _topk_ref(scores, k):
+    """tf.nn.top_k's set: k largest, threshold ties -> lower indices."""
+    order = np.lexsort((np.arange(len(scores)), -scores.astype(np.float64)))
+    return np.sort(order[:k])
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (1000, 1000), (5000, 37), (300000, 6000), (1 << 20, 6000), (4100, 4096)])
+def test_top_k_set(rb, cuda_device, n, k):
+    rng = np.random.default_rng(n + k)
+    for kind in ("uniform", "ties", "constant"):
+        if kind == "uniform":
+            s = rng.random(n).astype(np.float32)
+        elif kind == "ties":
+            s = (rng.integers(0, 50, n) / 50.0).astype(np.float32)     # the threshold always falls inside a tie class
+            s[::97] = -s[::97]
+        else:
+            s = np.full(n, 0.25, np.float32)
+        idx, val = rb.top_k_set(dev(s, cuda_device), k)
+        ref = _topk_ref(s, k)
+        assert np.array_equal(idx.cpu().numpy(), ref)
+        assert np.array_equal(val.cpu().numpy(), s[ref])
+
+
+def test_proposal_layer_matches_restated_graph(rb, cuda_device):
+    """top_k -> apply deltas -> clip -> min size -> NMS3D -> gather -> pad, against numpy + the NMS oracle."""
+    rng = np.random.default_rng(51)
+    n, pre, P, thr, depth = 120000, 6000, 1000, 0.7, 128
+    anchors = roi3d_synth.nms_boxes(n, (128, 128, 128), seed=52, side_px=(8.0, 64.0))[0]
+    deltas = (rng.standard_normal((n, 6)) * 0.5).astype(np.float32)
+    scores = rng.random(n).astype(np.float32)
+    scores[rng.integers(0, n, 2000)] = scores[rng.integers(0, n, 2000)]
+    std = (0.1, 0.1, 0.1, 0.2, 0.2, 0.2)
+    out, count = rb.proposal_layer(dev(scores, cuda_device), dev(deltas, cuda_device), dev(anchors, cuda_device), std, depth, pre, P, thr)
+    sel = _topk_ref(scores, pre)
+    # reference order: top_k sorted by (score desc, index asc); NMS ties follow that order
+    order = sel[np.lexsort((sel, -scores[sel].astype(np.float64)))]
+    boxes = oracle.decode_proposals(anchors, deltas, std, depth, order)
+    keep = oracle.non_max_suppression_3d(boxes, scores[order], P, thr)
+    ref = np.zeros((P, 6), np.float32)
+    ref[:len(keep)] = boxes[keep]
+    got = out.cpu().numpy()
+    assert int(count.item()) == len(keep)
+    assert np.allclose(got, ref, rtol=2e-6, atol=2e-7)          # decode uses expf (<= 2 ulp from numpy's exp)
