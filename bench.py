@@ -285,10 +285,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         if it >= 10:
             nms_ms.append(a.elapsed_time(b))
+    for _ in range(3):                                  # warm the workspace / pinned-buffer caches
+        rb.non_max_suppression_3d(nb, ns, 1000, 0.7)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(20):
+    for _ in range(50):
         kept = rb.non_max_suppression_3d(nb, ns, 1000, 0.7)
-    nms_e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    nms_e2e_ms = (time.perf_counter() - t0) / 50 * 1e3
     # batched: the 8 images of BASELINE cfg4 in one set of launches (ProposalLayer's batch_slice loop, core/models.py:487)
     nbb = torch.cat([d_nb] * 8)
     nsb = torch.cat([d_ns] * 8)
