@@ -525,3 +525,32 @@ def test_proposal_layer_matches_restated_graph(rb, cuda_device):
     got = out.cpu().numpy()
     assert int(count.item()) == len(keep)
     assert np.allclose(got, ref, rtol=2e-6, atol=2e-7)          # decode uses expf (<= 2 ulp from numpy's exp)
+
+
+def test_cfg3_large_volume_256(rb, cuda_device):
+    """BASELINE cfg3 scale: P2 of a 256^3 volume is [1,64,64,256,256] = 1.07 GB (32-bit element offsets must hold)."""
+    import torch
+    vol = (256, 256, 256)
+    shape = roi3d_synth.level_shape(vol, 2, batch=1)
+    assert int(np.prod(shape)) == 64 * 64 * 256 * 256
+    torch.manual_seed(3)
+    image = torch.randn(shape, device=cuda_device)
+    boxes = roi3d_synth.rois(48, vol, seed=3003, side_px=(8.0, 200.0))
+    boxes[0] = [0.97, 0.97, 0.97, 1.0, 1.0, 1.0]                # the far corner: largest offsets
+    bidx = np.zeros(48, np.int32)
+    tb, ti = dev(boxes, cuda_device), dev(bidx, cuda_device)
+    for crop in ((7, 7, 7), (14, 14, 14)):
+        out = rb.crop_and_resize_3d(image, tb, ti, crop)
+        pick = np.array([0, 1, 17, 47])
+        img_np = image.cpu().numpy()
+        ref = oracle.crop_and_resize_3d(img_np, boxes[pick], bidx[pick], crop)
+        assert np.array_equal(out[torch.from_numpy(pick).to(cuda_device)].cpu().numpy(), ref)
+        g = torch.randn_like(out)
+        gi = rb.crop_and_resize_3d_grad_image(g, tb, ti, shape)
+        lhs = float((out.double() * g.double()).sum())
+        rhs = float((image.double() * gi.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), float(out.double().norm() * g.double().norm()) * 1e-3)
+        del out, g, gi, img_np
+    # NMS3D at cfg3 size with the oracle (20000 -> 2000 @0.7)
+    nb, ns = roi3d_synth.nms_boxes(20000, vol)
+    assert np.array_equal(run_nms(rb, cuda_device, nb, ns, 2000, 0.7), oracle.non_max_suppression_3d(nb, ns, 2000, 0.7))
