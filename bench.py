@@ -407,7 +407,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "rois_per_step_per_gpu": total_rois, "l2": "inputs larger than L2 (feature maps + grads are %d MB per step; no explicit flush)" %
                    ((sum(t.numel() for t in images.values()) + sum(op["d_grads"].numel() for op in ops)) * 4 // 2 ** 20), "sharding": "one batch per GPU, no collective",
-                   "launch": "CUDA graph replay of the 16 C-ABI calls" if graph is not None else "eager C-ABI calls"},
+                   "launch": ("CUDA graph replay of the %d C-ABI calls" % (2 * len(ops))) if graph is not None else "eager C-ABI calls"},
         "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -507,8 +507,11 @@ def cpu_baseline(ops, kind, threads, sample_rois):
 
 
 def host_threads():
-    import oracle
-    return max(1, oracle.max_threads())
+    """Host cores available to this process (torchrun exports OMP_NUM_THREADS=1, which must not shrink the baseline)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def run_reference(args):
