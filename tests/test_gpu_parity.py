@@ -554,3 +554,31 @@ def test_cfg3_large_volume_256(rb, cuda_device):
     # NMS3D at cfg3 size with the oracle (20000 -> 2000 @0.7)
     nb, ns = roi3d_synth.nms_boxes(20000, vol)
     assert np.array_equal(run_nms(rb, cuda_device, nb, ns, 2000, 0.7), oracle.non_max_suppression_3d(nb, ns, 2000, 0.7))
+
+
+def test_car_random_shapes(rb, cuda_device):
+    """80 seeded random geometries (channels, volume dims, crop dims, weird boxes) through both kernel variants."""
+    rng = np.random.default_rng(2024)
+    for it in range(80):
+        C = int(rng.choice([1, 3, 4, 8, 12, 32, 36, 64, 96, 128, 256]))
+        B = int(rng.integers(1, 3))
+        H, W, D = (int(v) for v in rng.integers(1, 24, 3))
+        crop = tuple(int(v) for v in rng.integers(1, 18 if C > 64 else 30, 3))
+        n = int(rng.integers(0, 10))
+        spread = float(rng.choice([0.0, 0.4, 1.5]))
+        image = rng.standard_normal((B, H, W, D, C), dtype=np.float32)
+        boxes = (rng.random((n, 6)) * (1 + spread) - spread / 2).astype(np.float32)
+        if it % 3 == 0 and n:
+            boxes[:, 3:] = np.maximum(boxes[:, 3:], boxes[:, :3])           # ordered corners
+        bidx = rng.integers(0, B, n).astype(np.int32)
+        grads = rng.standard_normal((n,) + crop + (C,), dtype=np.float32)
+        ref = oracle.crop_and_resize_3d(image, boxes, bidx, crop, "trilinear", -2.0)
+        gref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape)
+        t = [dev(x, cuda_device) for x in (image, boxes, bidx, grads)]
+        for variant in (1, 2):
+            rb.custom_op.set_option("car_fwd_variant", variant)
+            rb.custom_op.set_option("car_bwd_variant", variant)
+            out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=-2.0).cpu().numpy()
+            assert np.array_equal(out, ref), (it, variant, C, (H, W, D), crop, n)
+            gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
+            assert rel_ok(gi, gref, BWD_TOL), (it, variant, C, (H, W, D), crop, n)

@@ -134,3 +134,56 @@ def test_iou_pairs_bit_exact():
     m = oracle.iou_matrix(bx)
     assert np.array_equal(ref.view(np.uint32), m[ii, jj].view(np.uint32))
     assert (ref > 0).sum() > 1000
+
+
+# ---- randomized shapes: the restatement must track the reference binaries everywhere, not just on the fixed cases ----
+try:
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    HAVE_HYP = True
+except Exception:  # noqa: BLE001
+    HAVE_HYP = False
+
+
+if HAVE_HYP:
+    dims = st.integers(min_value=1, max_value=7)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(B=st.integers(1, 2), H=dims, W=dims, D=dims, C=st.integers(1, 5), n=st.integers(0, 5),
+           ph=st.integers(1, 5), pw=st.integers(1, 5), pd=st.integers(1, 5), seed=st.integers(0, 10 ** 6),
+           spread=st.sampled_from([0.3, 1.0, 2.0]))
+    def test_random_shapes_bit_exact(B, H, W, D, C, n, ph, pw, pd, seed, spread):
+        r = np.random.default_rng(seed)
+        image = r.standard_normal((B, H, W, D, C), dtype=np.float32)
+        # corners anywhere in [-spread/2, 1+spread/2]: reversed, degenerate and out-of-range boxes included
+        boxes = (r.random((n, 6)) * (1 + spread) - spread / 2).astype(np.float32)
+        if n:
+            boxes[0, r.integers(0, 6)] = np.float32(r.integers(0, 2))          # exact 0 / 1 coordinates
+        bi = r.integers(0, B, n).astype(np.int32)
+        g = r.standard_normal((n, ph, pw, pd, C), dtype=np.float32)
+        crop = (ph, pw, pd)
+        assert np.array_equal(REF.crop_and_resize_3d(image, boxes, bi, crop, "trilinear", 0.5),
+                              oracle.crop_and_resize_3d(image, boxes, bi, crop, "trilinear", 0.5))
+        for method in ("trilinear", "nearest"):
+            assert np.array_equal(REF.crop_and_resize_3d_grad_image(g, boxes, bi, image.shape, method),
+                                  oracle.crop_and_resize_3d_grad_image(g, boxes, bi, image.shape, method))
+        assert np.array_equal(REF.crop_and_resize_3d_grad_boxes(g, image, boxes, bi),
+                              oracle.crop_and_resize_3d_grad_boxes(g, image, boxes, bi), equal_nan=True)
+        if pw == pd:
+            assert np.array_equal(REF.crop_and_resize_3d(image, boxes, bi, crop, "nearest", 0.5),
+                                  oracle.crop_and_resize_3d(image, boxes, bi, crop, "nearest", 0.5))
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(1, 300), max_out=st.integers(0, 320), thr=st.floats(0.0, 1.0, width=32),
+           levels=st.sampled_from([0, 3, 17]), seed=st.integers(0, 10 ** 6))
+    def test_random_nms_bit_exact(n, max_out, thr, levels, seed):
+        r = np.random.default_rng(seed)
+        c = r.random((n, 3)) * 0.6 + 0.2
+        s = r.random((n, 3)) * 0.5
+        boxes = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+        flip = r.random(n) < 0.2
+        boxes[flip] = boxes[flip][:, [3, 4, 5, 0, 1, 2]]
+        zero = r.random(n) < 0.05
+        boxes[zero, 3] = boxes[zero, 0]                                        # zero-volume boxes (re-push quirk)
+        scores = r.random(n).astype(np.float32) if levels == 0 else (r.integers(0, levels, n) / levels).astype(np.float32)
+        assert np.array_equal(REF.non_max_suppression_3d(boxes, scores, max_out, thr),
+                              oracle.non_max_suppression_3d(boxes, scores, max_out, thr))
