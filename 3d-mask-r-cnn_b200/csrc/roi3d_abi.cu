@@ -17,6 +17,7 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_bwd_variant")) return OPT_CAR_BWD_VARIANT;
     if (!strcmp(name, "nms_variant")) return OPT_NMS_VARIANT;
     if (!strcmp(name, "car_lanes_v")) return OPT_CAR_V;
+    if (!strcmp(name, "car_ctas_per_sm_target")) return OPT_KSPLIT;
     return -1;
 }
 

@@ -318,6 +318,23 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
                 }
             }
             __syncthreads();
+            // ---- L2 prefetch of the next depth sample's footprint: its stage A then finds the taps in L2 ----
+            if (k + 1 < k1 && (lane & 7) == 0) {
+                const float in_zn = axis_coord(z1, z2, g.D, g.pd, k + 1, zscale);
+                if (!axis_invalid(in_zn, g.D)) {
+                    const unsigned zfn = (unsigned)(int)floorf(in_zn) * g.C, zcn = (unsigned)(int)ceilf(in_zn) * g.C;
+                    for (int idx = slot; idx < nvox; idx += vs) {
+                        const float *p = img + lds32u(voff_u32 + idx * 4);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if (von[v]) {
+                                if (zfn != zf && zfn != zc) prefetch_l2(p + zfn + v * vstep);
+                                if (zcn != zf && zcn != zc) prefetch_l2(p + zcn + v * vstep);
+                            }
+                        }
+                    }
+                }
+            }
             // ---- stage B: x-lerp, y-lerp from the plane -> crops ----------------------
 #pragma unroll 2
             for (int idx = slot; idx < nout; idx += vs, o += ostride) {
@@ -499,6 +516,15 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
                 }
             }
             __syncthreads();
+            // ---- L2 prefetch of the next depth sample's grads slice ----------------------------
+            if (k + 1 < k1 && (lane & 7) == 0) {
+                const float *gn = gcrop + (((long long)ya * g.pw + slot) * g.pd + (k + 1)) * g.C;
+                for (int idx = slot; idx < nent; idx += vs, gn += gstride) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (von[v]) prefetch_l2(gn + v * vstep);
+                }
+            }
             // ---- stage B': every footprint voxel gathers its weighted sum, then 2 REDs ------
             for (int idx = slot; idx < nvox; idx += vs) {
                 const int rr = (int)(((float)idx + 0.5f) * rnx), cx = idx - rr * nx, r = rlo + rr;
@@ -561,7 +587,7 @@ static void pick_lanes(const CarGeom &g, int &cl, int &V) {
 }
 
 static int pick_ksplits(const CarGeom &g, int chunks) {
-    const long long want = (long long)kNumSMs * 16;
+    const long long want = (long long)kNumSMs * (option_value(OPT_KSPLIT) > 0 ? option_value(OPT_KSPLIT) : 16);
     const long long per = (long long)g.n * chunks;
     long long ks = (want + per - 1) / per;
     if (ks < 1) ks = 1;

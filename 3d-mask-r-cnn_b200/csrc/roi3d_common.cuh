@@ -16,7 +16,7 @@ namespace roi3d {
 extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
-enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_COUNT };
+enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_COUNT };
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -74,6 +74,11 @@ __device__ __forceinline__ void red_add4(float *p, const float4 v) {
 }
 __device__ __forceinline__ void red_add1(float *p, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// pull one 128-byte line towards L2 ahead of its use (no register, no scoreboard entry)
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 // ---- shared memory through 32-bit addresses (no generic->shared window math in the loops) ----

@@ -189,6 +189,8 @@ ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, 
  *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
  *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane kernels
  *   "nms_variant"       reserved
+ *   "car_ctas_per_sm_target"   grid sizing of the plane kernels: depth-sample splits are chosen so that about this
+ *                       many CTAs per SM exist (0 = default 16)
  * Returns ROI3D_EINVAL for an unknown name.  roi3d_kernel_launches() returns
  * the number of kernel launches this library has enqueued on the calling
  * thread since the last roi3d_reset_kernel_launches().
