@@ -20,7 +20,7 @@
  * call-outs) and runs the reference's OWN Compute() functions and its own
  * IOU<float>.  tests/test_oracle_pin.py asserts that every function below is
  * bit-identical to them (forward, grad-image, grad-boxes, NMS, 200k IoU
- * pairs; edge cases included), and tests/golden/*.npz were written by
+ * pairs; edge cases included), and the tests/golden npz files were written by
  * `make_golden.py --check-ref`, i.e. only after the same check passed.
  * Two reference defects found that way are documented where they apply:
  * the grad-boxes depth step (restated faithfully) and the `nearest` forward
