@@ -110,6 +110,11 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
     // measured on B200 (profiles/variants_r1.txt): the plane-staged kernel wins once a depth slice has
     // enough outputs to amortise its per-CTA tables (14^3: 2.1x), the direct gather wins at 7^3
     if (variant == 0) variant = (plane_ok && C >= 32 && ph * pw >= 100) ? 2 : 1;
+    if (variant == 3 && plane_ok) {                                     // TMA-fed plane kernel (opt-in)
+        const int rc = launch_car3d_fwd_plane_tma(image, boxes, box_index, g, extrapolation_value, crops, s);
+        if (rc != ROI3D_EUNSUPPORTED) return rc;
+        variant = 2;
+    }
     if (variant == 2 && plane_ok) return launch_car3d_fwd_plane(image, boxes, box_index, g, extrapolation_value, crops, s);
     return launch_car3d_fwd_direct(image, boxes, box_index, g, method, extrapolation_value, crops, s);
 }

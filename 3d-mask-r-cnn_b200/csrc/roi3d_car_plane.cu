@@ -363,6 +363,167 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
 }
 
 // ---------------------------------------------------------------------------------
+// forward, TMA-fed (variant 3).  Same tables and arithmetic; stage A's gather is done by the TMA engine: one warp
+// issues a bulk copy (cp.async.bulk, 256-byte channel-chunk row per footprint voxel and z tap) for the NEXT depth
+// sample into a raw buffer right after the current sample has been z-lerped out of it, so the copies fly while all
+// eight warps run stage B.  No registers and no LSU issue slots are spent on the gather; completion is an mbarrier.
+// ---------------------------------------------------------------------------------
+template <bool PYR>
+__global__ void __launch_bounds__(PL_THREADS, 3)
+car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
+                           const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
+                           float *__restrict__ crops, const PyrParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    size_t off = 0;
+    PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
+    OutEntry *otab = reinterpret_cast<OutEntry *>(smem_raw + off); off += sizeof(OutEntry) * (size_t)L.otab;
+    unsigned *voff = reinterpret_cast<unsigned *>(smem_raw + off); off += (sizeof(unsigned) * (size_t)L.zcap + 15) & ~size_t(15);
+    off = (off + 127) & ~size_t(127);
+    const unsigned ebytes = (unsigned)L.cl * 16;
+    unsigned char *Rf = smem_raw + off; off += (size_t)L.zcap * ebytes;      // raw floor-z taps
+    unsigned char *Rc = smem_raw + off; off += (size_t)L.zcap * ebytes;      // raw ceil-z taps
+    unsigned char *Zraw = smem_raw + off; off += (size_t)L.zcap * ebytes;    // z-lerped plane
+    __shared__ __align__(8) unsigned long long s_mbar;
+
+    int bid = blockIdx.x;
+    const int chunk = bid % L.chunks; bid /= L.chunks;
+    const int ks = bid % L.ksplits;
+    const int b = bid / L.ksplits;
+    __shared__ int s_level;
+    if constexpr (PYR) {
+        if (threadIdx.x == 0) {
+            float b6[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) b6[q] = __ldg(boxes + (size_t)b * 6 + q);
+            const PyrRoute r = pyr_route(b6, P);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) S.box[q] = r.box[q];
+            s_level = r.level - 2;
+        }
+        __syncthreads();
+        const int lv = s_level;
+        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
+        image = P.image[lv];
+    } else {
+        if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
+        __syncthreads();
+    }
+    const unsigned mbar = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    build_axis_tables(S, g);
+    build_y_tiles(S, g, L.zcap);
+
+    const AxisTab &Y = S.ax[0], &X = S.ax[1];
+    const int nx = X.n;
+    const int cl = L.cl;
+    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
+    const int c4 = chunk * cl + lane;
+    const bool on = c4 < g.C / 4;
+    const unsigned rowbytes = (unsigned)min(cl, g.C / 4 - chunk * cl) * 16;  // bytes of this chunk actually present
+    const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
+    const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
+    const float *img_chunk = image + (long long)bimg * g.H * sH + chunk * cl * 4;   // lane-independent: TMA source
+    float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
+    const float4 ext4 = make_float4(ext, ext, ext, ext);
+    const float z1 = S.box[2], z2 = S.box[5];
+    const float zscale = axis_scale(z1, z2, g.D, g.pd);
+    const int kper = (g.pd + L.ksplits - 1) / L.ksplits;
+    const int k0 = min(ks * kper, g.pd), k1 = min(g.pd, k0 + kper);
+    const unsigned rf_u32 = smem_u32(Rf), rc_u32 = smem_u32(Rc);
+    const unsigned z_u32 = smem_u32(Zraw) + lane * 16;
+    const unsigned otab_u32 = smem_u32(otab), voff_u32 = smem_u32(voff);
+    const long long ostride = (long long)vs * g.pd * g.C;
+    unsigned parity = 0;
+
+    for (int tl = 0; tl < S.ntiles; ++tl) {
+        const int ya = S.tile_y0[tl], yb = S.tile_y0[tl + 1];
+        const int r0 = S.tile_r0[tl], r1 = S.tile_r1[tl];
+        const int nvox = (r1 >= r0) ? (r1 - r0 + 1) * nx : 0;
+        const int nout = (yb - ya) * g.pw;
+        for (int idx = threadIdx.x; idx < nvox; idx += PL_THREADS) {
+            const int r = idx / nx, cx = idx - r * nx;
+            voff[idx] = (unsigned)Y.list[r0 + r] * sH + (unsigned)X.list[cx] * sW;
+        }
+        for (int idx = threadIdx.x; idx < nout; idx += PL_THREADS) {
+            const int yy = idx / g.pw, x = idx - yy * g.pw, y = ya + yy;
+            const int py0 = Y.pos0[y], px0 = X.pos0[x];
+            OutEntry e;
+            if (py0 < 0 || px0 < 0) {
+                e.o_top = 0xFFFFFFFFu; e.o_bot = 0xFFFFFFFFu; e.xl = 0.f; e.yl = 0.f;
+            } else {
+                const unsigned rt_ = (unsigned)(py0 - r0) * nx, rb = (unsigned)(Y.pos1[y] - r0) * nx;
+                const unsigned px1 = (unsigned)X.pos1[x];
+                e.o_top = ((rt_ + px0) * ebytes) | (((rt_ + px1) * ebytes) << 16);
+                e.o_bot = ((rb + px0) * ebytes) | (((rb + px1) * ebytes) << 16);
+                e.xl = X.t[x]; e.yl = Y.t[y];
+            }
+            otab[idx] = e;
+        }
+        __syncthreads();                                       // tables (and the mbarrier init) visible
+
+        // warp 0 gathers depth sample k into the raw buffers with bulk copies
+        auto issue = [&](int k) {
+            if (threadIdx.x < 32) {
+                const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
+                const unsigned zf = (unsigned)(int)floorf(in_z) * g.C, zc = (unsigned)(int)ceilf(in_z) * g.C;
+                fence_proxy_async();                           // earlier generic reads of the raw buffers are done
+                if (threadIdx.x == 0) mbar_expect_tx(mbar, 2u * (unsigned)nvox * rowbytes);
+                __syncwarp();
+                for (int idx = threadIdx.x; idx < nvox; idx += 32) {
+                    const float *p = img_chunk + voff[idx];
+                    bulk_g2s(rf_u32 + idx * ebytes, p + zf, rowbytes, mbar);
+                    bulk_g2s(rc_u32 + idx * ebytes, p + zc, rowbytes, mbar);
+                }
+            }
+        };
+        auto zvalid = [&](int k) { return k < k1 && nvox > 0 && !axis_invalid(axis_coord(z1, z2, g.D, g.pd, k, zscale), g.D); };
+
+        int kfirst = k0;
+        while (kfirst < k1 && !zvalid(kfirst)) ++kfirst;
+        if (kfirst < k1) issue(kfirst);
+
+        for (int k = k0; k < k1; ++k) {
+            float *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
+            if (!zvalid(k)) {
+                if (on)
+                    for (int idx = slot; idx < nout; idx += vs, o += ostride) st_stream4(o, ext4);
+                continue;
+            }
+            const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
+            const float zl = __fsub_rn(in_z, floorf(in_z));
+            mbar_wait(mbar, parity);                           // the taps of sample k have landed
+            parity ^= 1u;
+            if (on) {
+                for (int idx = slot; idx < nvox; idx += vs) {
+                    const float4 f = lds128(rf_u32 + idx * ebytes + lane * 16);
+                    const float4 c = lds128(rc_u32 + idx * ebytes + lane * 16);
+                    sts128(z_u32 + idx * ebytes, lerp_rn(f, c, zl));
+                }
+            }
+            __syncthreads();                                   // plane complete, raw buffers free
+            if (zvalid(k + 1)) issue(k + 1);                   // flies during stage B
+            if (on) {
+#pragma unroll 2
+                for (int idx = slot; idx < nout; idx += vs, o += ostride) {
+                    const uint4 e = lds128u(otab_u32 + idx * 16);
+                    const bool bad = e.x == 0xFFFFFFFFu;
+                    const unsigned et = bad ? 0u : e.x, eb = bad ? 0u : e.y;
+                    const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
+                    const float4 tlv = lds128(z_u32 + (et & 0xFFFFu)), trv = lds128(z_u32 + (et >> 16));
+                    const float4 blv = lds128(z_u32 + (eb & 0xFFFFu)), brv = lds128(z_u32 + (eb >> 16));
+                    const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
+                    float4 res = sel4(bad, ext4, lerp_rn(top, bot, yl));
+                    if constexpr (PYR) res = scrub4(res);
+                    st_stream4(o, res);
+                }
+            }
+            __syncthreads();                                   // plane free for the next sample
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // backward (grad image).  grad_image must be zero-filled before the launch.
 // ---------------------------------------------------------------------------------
 struct __align__(8) Contrib { unsigned off; float w; };   // staged-slice byte offset of a sample, its weight
@@ -630,6 +791,32 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
                            float ext, float *crops, cudaStream_t stream)
 {
     return launch_fwd_plane_impl(image, boxes, box_index, g, ext, crops, nullptr, stream);
+}
+
+int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                               float ext, float *crops, cudaStream_t stream)
+{
+    PlaneLaunch L;
+    L.cl = 16;
+    while (L.cl > 1 && L.cl / 2 >= g.C / 4) L.cl /= 2;
+    const int nxmax = min(2 * g.pw, g.W);
+    L.otab = min(g.ph * g.pw, max(PL_MAXOUT, g.pw));
+    const size_t eb = (size_t)L.cl * 16;
+    L.zcap = (int)max((size_t)2 * nxmax, (size_t)(22 * 1024) / eb);       // 3 buffers of ~22 KB
+    if ((size_t)L.zcap * eb > 65535) return ROI3D_EUNSUPPORTED;
+    const size_t smem = a16(sizeof(PlaneShared)) + sizeof(OutEntry) * (size_t)L.otab + a16(sizeof(unsigned) * (size_t)L.zcap) +
+                        128 + 3 * (size_t)L.zcap * eb;
+    if (smem > 200 * 1024) return ROI3D_EUNSUPPORTED;
+    L.chunks = (g.C / 4 + L.cl - 1) / L.cl;
+    L.ksplits = pick_ksplits(g, L.chunks);
+    auto kern = car3d_fwd_plane_tma_kernel<false>;
+    if (smem > 48 * 1024)
+        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (long long)g.n * L.ksplits * L.chunks;
+    if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, PyrParams{});
+    ROI3D_LAUNCH_CHECK();
+    return ROI3D_OK;
 }
 
 static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,

@@ -169,7 +169,7 @@ CAR_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])                  # direct, plane-staged, plane-staged fed by TMA bulk copies
 @pytest.mark.parametrize("case", CAR_CASES)
 def test_car_forward_matches_oracle(rb, cuda_device, case, variant):
     B, H, W, D, C, n, crop = case
@@ -580,5 +580,9 @@ def test_car_random_shapes(rb, cuda_device):
             rb.custom_op.set_option("car_bwd_variant", variant)
             out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=-2.0).cpu().numpy()
             assert np.array_equal(out, ref), (it, variant, C, (H, W, D), crop, n)
+            if variant == 2:
+                rb.custom_op.set_option("car_fwd_variant", 3)
+                out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=-2.0).cpu().numpy()
+                assert np.array_equal(out, ref), (it, 3, C, (H, W, D), crop, n)
             gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
             assert rel_ok(gi, gref, BWD_TOL), (it, variant, C, (H, W, D), crop, n)
