@@ -18,7 +18,8 @@ LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libroi3d_b200.so")
 HEADER = os.path.join(_ROOT, "include", "roi3d.h")
 
-SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_nms.cu", "roi3d_boxes.cu"]
+SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_nms.cu", "roi3d_boxes.cu",
+           "roi3d_detect.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",      # Blackwell B200 only
     "-O3", "-lineinfo", "-std=c++17",
@@ -33,6 +34,8 @@ EXPORTS = [
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
     "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
     "roi3d_topk_workspace_bytes", "roi3d_topk", "roi3d_gather_pad_boxes",
+    "roi3d_refine_detections_workspace_bytes", "roi3d_refine_detections", "roi3d_mask_targets",
+    "roi3d_pack_f16", "roi3d_unpack_f16", "roi3d_pack_bits", "roi3d_unpack_bits",
     "roi3d_set_option", "roi3d_get_option", "roi3d_kernel_launches", "roi3d_reset_kernel_launches",
 ]
 
@@ -108,6 +111,16 @@ def _declare(lib):
     lib.roi3d_topk.argtypes = [vp, i, i, vp, vp, vp, sz, vp]
     lib.roi3d_gather_pad_boxes.restype = i
     lib.roi3d_gather_pad_boxes.argtypes = [vp, vp, vp, i, vp, vp]
+    ll = ctypes.c_longlong
+    lib.roi3d_refine_detections_workspace_bytes.restype = sz
+    lib.roi3d_refine_detections_workspace_bytes.argtypes = [i, i, i]
+    lib.roi3d_refine_detections.restype = i
+    lib.roi3d_refine_detections.argtypes = [vp, vp, vp, i, i, i, vp, vp, f, f, i, vp, vp, vp, sz, vp]
+    lib.roi3d_mask_targets.restype = i
+    lib.roi3d_mask_targets.argtypes = [vp, i, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp]
+    for name in ("roi3d_pack_f16", "roi3d_unpack_f16", "roi3d_pack_bits", "roi3d_unpack_bits"):
+        getattr(lib, name).restype = i
+        getattr(lib, name).argtypes = [vp, ll, vp, vp]
     lib.roi3d_set_option.restype = i
     lib.roi3d_set_option.argtypes = [ctypes.c_char_p, i]
     lib.roi3d_get_option.restype = i

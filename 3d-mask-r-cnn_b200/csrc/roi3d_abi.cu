@@ -190,6 +190,75 @@ int roi3d_gather_pad_boxes(const float *boxes, const int *keep_idx, const int *k
     return launch_gather_pad_boxes(boxes, keep_idx, keep_count, proposal_count, proposals, static_cast<cudaStream_t>(stream));
 }
 
+size_t roi3d_refine_detections_workspace_bytes(int images, int rois_per_image, int max_instances)
+{
+    if (images <= 0 || rois_per_image < 0 || max_instances < 0) return 256;
+    return refine_detections_workspace_bytes(images, rois_per_image, max_instances);
+}
+
+int roi3d_refine_detections(const float *rois, const float *probs, const float *deltas, int images, int rois_per_image,
+                            int num_classes, const float image_shape[3], const float std_dev[6], float min_confidence,
+                            float nms_threshold, int max_instances, float *detections, int *det_count, void *workspace,
+                            size_t workspace_bytes, roi3d_stream_t stream)
+{
+    if (images < 0 || rois_per_image < 0 || num_classes < 2 || max_instances < 0 || !image_shape || !std_dev) return ROI3D_EINVAL;
+    if (!(nms_threshold >= 0.0f && nms_threshold <= 1.0f)) return ROI3D_EINVAL;
+    if (!(image_shape[0] > 0.0f && image_shape[1] > 0.0f && image_shape[2] > 0.0f)) return ROI3D_EINVAL;
+    if (images == 0 || max_instances == 0) return ROI3D_OK;
+    if (!detections || (rois_per_image > 0 && (!rois || !probs || !deltas))) return ROI3D_EINVAL;
+    if ((long long)images * max_instances * 8 > 0x7fffffffll || (long long)images * rois_per_image > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
+    return launch_refine_detections(rois, probs, deltas, images, rois_per_image, num_classes, image_shape, std_dev,
+                                    min_confidence, nms_threshold, max_instances, detections, det_count, workspace,
+                                    workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_mask_targets(const void *masks, int mask_dtype, int G, int H, int W, int D, const float *boxes,
+                       const int *assignment, int n, int mh, int mw, int md, float *targets, unsigned char *bits,
+                       roi3d_stream_t stream)
+{
+    if (G < 0 || H <= 0 || W <= 0 || D <= 0 || n < 0 || mh <= 0 || mw <= 0 || md <= 0) return ROI3D_EINVAL;
+    if (mask_dtype != ROI3D_MASK_F32 && mask_dtype != ROI3D_MASK_U8) return ROI3D_EINVAL;
+    if (!targets && !bits) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!masks || !boxes || G == 0) return ROI3D_EINVAL;
+    if (reinterpret_cast<uintptr_t>(bits) & 3) return ROI3D_EINVAL;
+    if ((long long)H * W * D > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
+    return launch_mask_targets(masks, mask_dtype, H, W, D, boxes, assignment, n, mh, mw, md, targets, bits,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_pack_f16(const float *x, long long n, void *half_out, roi3d_stream_t stream)
+{
+    if (n < 0) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!x || !half_out || (reinterpret_cast<uintptr_t>(half_out) & 1) || (reinterpret_cast<uintptr_t>(x) & 3)) return ROI3D_EINVAL;
+    return launch_f32_to_f16(x, n, half_out, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_unpack_f16(const void *half_in, long long n, float *y, roi3d_stream_t stream)
+{
+    if (n < 0) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!half_in || !y || (reinterpret_cast<uintptr_t>(half_in) & 1) || (reinterpret_cast<uintptr_t>(y) & 3)) return ROI3D_EINVAL;
+    return launch_f16_to_f32(half_in, n, y, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_pack_bits(const float *x, long long n, unsigned char *bits, roi3d_stream_t stream)
+{
+    if (n < 0) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!x || !bits || (reinterpret_cast<uintptr_t>(bits) & 3)) return ROI3D_EINVAL;
+    return launch_pack_bits(x, n, bits, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y, roi3d_stream_t stream)
+{
+    if (n < 0) return ROI3D_EINVAL;
+    if (n == 0) return ROI3D_OK;
+    if (!bits || !y) return ROI3D_EINVAL;
+    return launch_unpack_bits(bits, n, y, static_cast<cudaStream_t>(stream));
+}
+
 static int pyramid_check(const int level_shapes[4][3], int B, int C, const float *boxes, int rois_per_image,
                          const float image_shape[3], int ph, int pw, int pd)
 {

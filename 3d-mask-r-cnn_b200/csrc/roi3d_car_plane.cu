@@ -374,7 +374,7 @@ car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restr
                            const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
                            float *__restrict__ crops, const PyrParams P)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
     PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
     OutEntry *otab = reinterpret_cast<OutEntry *>(smem_raw + off); off += sizeof(OutEntry) * (size_t)L.otab;

@@ -165,6 +165,17 @@ int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_o
                 cudaStream_t stream);
 int launch_gather_pad_boxes(const float *boxes, const int *keep, const int *count, int p, float *out, cudaStream_t stream);
 size_t nms3d_workspace_bytes(int n, int segments);
+size_t refine_detections_workspace_bytes(int images, int rois, int max_inst);
+int launch_refine_detections(const float *rois, const float *probs, const float *deltas, int images, int rois_per_image,
+                             int num_classes, const float image_shape[3], const float std_dev[6], float min_conf,
+                             float nms_thr, int max_inst, float *detections, int *det_count, void *ws, size_t ws_bytes,
+                             cudaStream_t stream);
+int launch_mask_targets(const void *masks, int mask_dtype, int H, int W, int D, const float *boxes, const int *assignment,
+                        int n, int mh, int mw, int md, float *targets, unsigned char *bits, cudaStream_t stream);
+int launch_f32_to_f16(const float *x, long long n, void *y, cudaStream_t stream);
+int launch_f16_to_f32(const void *x, long long n, float *y, cudaStream_t stream);
+int launch_pack_bits(const float *x, long long n, unsigned char *bits, cudaStream_t stream);
+int launch_unpack_bits(const unsigned char *bits, long long n, float *y, cudaStream_t stream);
 int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets, int segments, int n, int max_out,
                  float thr, int *keep_idx, int *keep_count, void *ws, size_t ws_bytes, cudaStream_t stream);
 

@@ -575,6 +575,116 @@ def proposal_layer(scores, deltas, anchors, std_dev, image_depth, pre_nms_limit,
 
 
 # ---------------------------------------------------------------------------------------
+# DetectionLayer, mask targets and the target files' payloads
+# ---------------------------------------------------------------------------------------
+def refine_detections(rois, probs, deltas, image_shape, detection_min_confidence, detection_nms_threshold,
+                      bbox_std_dev=None, detection_max_instances=None, return_counts=False):
+    """``refine_detections_graph`` (core/models.py:1415-1524) / ``DetectionLayer.call`` (:1552-1575) on the device.
+
+    ``rois [R,6]`` / ``probs [R,K]`` / ``deltas [R,K,6]`` for one image, or with a leading batch axis for the whole
+    layer (one set of launches, no ``batch_slice`` loop, no host sync).  ``image_shape`` = (H, W, D) in pixels.
+    Returns ``detections [max_instances, 8]`` (or ``[B, max_instances, 8]``) =
+    ``(y1,x1,z1,y2,x2,z2,class_id,score)`` normalised, zero padded.  The NMS is the 3-D op (row f3), where the fork
+    calls the 2-D ``tf.image.non_max_suppression`` on (y, x)."""
+    dev = _device()
+    r, p, d = _Arg(rois, torch.float32, dev), _Arg(probs, torch.float32, dev), _Arg(deltas, torch.float32, dev)
+    single = r.dev.dim() == 2
+    _require(r.dev.dim() in (2, 3) and r.dev.shape[-1] == 6, "rois must be [R, 6] or [B, R, 6]")
+    _require(p.dev.dim() == r.dev.dim() and tuple(p.dev.shape[:-1]) == tuple(r.dev.shape[:-1]), "probs has incompatible shape")
+    K = int(p.dev.shape[-1])
+    _require(K >= 2, "probs needs a foreground class column")
+    _require(tuple(d.dev.shape) == tuple(r.dev.shape[:-1]) + (K, 6), "deltas has incompatible shape")
+    B, R = (1, int(r.dev.shape[0])) if single else (int(r.dev.shape[0]), int(r.dev.shape[1]))
+    std = [0.1, 0.1, 0.1, 0.2, 0.2, 0.2] if bbox_std_dev is None else [float(v) for v in bbox_std_dev]
+    M = 200 if detection_max_instances is None else int(detection_max_instances)
+    thr = float(detection_nms_threshold)
+    _require(0.0 <= thr <= 1.0, "iou_threshold must be in [0, 1]")
+    lib = _lib.load()
+    det = torch.empty((B, M, 8), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    if B and M:
+        ws = torch.empty(lib.roi3d_refine_detections_workspace_bytes(B, R, M), dtype=torch.uint8, device=dev)
+        shp = (ctypes.c_float * 3)(*[float(v) for v in list(image_shape)[:3]])
+        _lib.check(lib.roi3d_refine_detections(_ptr(r.dev), _ptr(p.dev), _ptr(d.dev), B, R, K, shp, (ctypes.c_float * 6)(*std),
+                                               float(detection_min_confidence), thr, M, _ptr(det), _ptr(cnt), _ptr(ws),
+                                               ws.numel(), _stream_ptr()))
+    out = det[0] if single else det
+    host = r.host or p.host or d.host
+    out = _finish(out, host, r.numpy)
+    if return_counts:
+        return out, _finish(cnt, host, r.numpy)
+    return out
+
+
+def mask_targets(gt_masks, boxes, assignment, mask_shape, packed=False):
+    """``detection_targets_graph._get_masks`` (core/models.py:972-1005) in one kernel: the ground-truth mask assigned
+    to each positive ROI (``gt_masks [G,H,W,D]``, float32 or uint8/bool; ``assignment`` int32 ``[N]`` or None for
+    ``range(N)``) is cropped to ``boxes [N,6]`` at ``mask_shape`` and rounded.  Returns float32 ``[N,mh,mw,md]``;
+    with ``packed=True`` also the ``numpy.packbits`` payload of the target file (uint8 ``[ceil(N*mh*mw*md/8)]``)."""
+    dev = _device()
+    g = gt_masks if isinstance(gt_masks, torch.Tensor) else torch.as_tensor(np.asarray(gt_masks))
+    if g.dtype == torch.bool:
+        g = g.to(torch.uint8)
+    m = _Arg(g, torch.uint8 if g.dtype == torch.uint8 else torch.float32, dev)
+    b = _Arg(boxes, torch.float32, dev)
+    _require(m.dev.dim() == 4, "gt_masks must be [G, H, W, D]")
+    _require(b.dev.dim() == 2 and b.dev.shape[1] == 6, "boxes must have 6 columns")
+    a = _Arg(assignment, torch.int32, dev).dev if assignment is not None else None
+    n = int(b.dev.shape[0])
+    _require(a is None or tuple(a.shape) == (n,), "assignment has incompatible shape")
+    mh, mw, md = _crop_size(mask_shape)
+    G, H, W, D = (int(v) for v in m.dev.shape)
+    out = torch.empty((n, mh, mw, md), dtype=torch.float32, device=dev)
+    bits = torch.empty((n * mh * mw * md + 7) // 8, dtype=torch.uint8, device=dev) if packed else None
+    _lib.check(_lib.load().roi3d_mask_targets(_ptr(m.dev), 1 if m.dev.dtype == torch.uint8 else 0, G, H, W, D, _ptr(b.dev),
+                                              _ptr(a) if a is not None else None, n, mh, mw, md, _ptr(out),
+                                              _ptr(bits) if packed else None, _stream_ptr()))
+    host = m.host or b.host
+    res = _finish(out, host, b.numpy)
+    return (res, _finish(bits, host, b.numpy)) if packed else res
+
+
+def pack_f16(x):
+    """``x.astype(np.float16)`` on the device (round to nearest even): the ``rois_aligned`` payload, core/models.py:3613."""
+    dev = _device()
+    a = _Arg(x, torch.float32, dev)
+    out = torch.empty(a.dev.shape, dtype=torch.float16, device=dev)
+    _lib.check(_lib.load().roi3d_pack_f16(_ptr(a.dev), a.dev.numel(), _ptr(out), _stream_ptr()))
+    return _finish(out, a.host, a.numpy)
+
+
+def unpack_f16(x):
+    """float16 -> float32 on the device (the reader's ``astype(np.float32)``, core/data_generators.py:245)."""
+    dev = _device()
+    a = _Arg(x, torch.float16, dev)
+    out = torch.empty(a.dev.shape, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().roi3d_unpack_f16(_ptr(a.dev), a.dev.numel(), _ptr(out), _stream_ptr()))
+    return _finish(out, a.host, a.numpy)
+
+
+def pack_bits(x):
+    """``_bitpack`` (core/models.py:3585-3595): ``(numpy.packbits((x > 0.5).reshape(-1)), shape int32)``."""
+    dev = _device()
+    a = _Arg(x, torch.float32, dev)
+    n = a.dev.numel()
+    bits = torch.empty((n + 7) // 8, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().roi3d_pack_bits(_ptr(a.dev), n, _ptr(bits), _stream_ptr()))
+    return _finish(bits, a.host, a.numpy), np.array(tuple(a.dev.shape), dtype=np.int32)
+
+
+def unpack_bits(bits, shape):
+    """``_unbit`` (core/data_generators.py:1908-1921): packed uint8 -> float32 0/1 array of ``shape`` on the device."""
+    dev = _device()
+    a = _Arg(bits, torch.uint8, dev)
+    shape = tuple(int(v) for v in shape)
+    n = int(np.prod(shape)) if shape else 1
+    _require(a.dev.numel() * 8 >= n, "bits too short for shape")
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().roi3d_unpack_bits(_ptr(a.dev), n, _ptr(out), _stream_ptr()))
+    return _finish(out, a.host, a.numpy)
+
+
+# ---------------------------------------------------------------------------------------
 # tuning / introspection passthroughs
 # ---------------------------------------------------------------------------------------
 def set_option(name, value):

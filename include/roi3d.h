@@ -182,10 +182,57 @@ ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, 
                                      const float std_dev[6], float image_depth, float *boxes, roi3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * DetectionLayer on the device
+ * replaces: refine_detections_graph + the utils.batch_slice loop of DetectionLayer.call, core/models.py:1415-1575, for
+ *           the whole batch in one set of launches, with the 3-D op as the NMS (the fork calls the 2-D
+ *           tf.image.non_max_suppression on y/x, :1496-1501; utils.non_max_suppression_3d_graph, core/utils.py:467-503,
+ *           is the wrapper the 3-D op was meant to be reached through).
+ * rois [B,R,6] normalised, probs [B,R,num_classes], deltas [B,R,num_classes,6] (device, float32).  As in this fork
+ * the class is always 1 (fg_probs = probs[:,1], :1441).  Per ROI: score >= min_confidence, deltas * std_dev,
+ * apply_box_deltas_3d_graph in pixels (core/utils.py:412-464), clip to [0,H]x[0,W]x[0,D], sizes >= (1,1,0.5) px; NMS
+ * with max_instances outputs; rows in selection order = descending score (the graph's top_k is then the identity);
+ * boxes back to normalised coordinates clipped to [0,1]; rows past the kept count are zero.
+ * detections [B,max_instances,8] = (y1,x1,z1,y2,x2,z2,class_id,score); det_count [B] (device, optional, may be NULL).
+ * image_shape / std_dev are host arrays.  No host synchronisation.  workspace:
+ * roi3d_refine_detections_workspace_bytes(B, R, max_instances), 256-byte aligned.
+ * ------------------------------------------------------------------------- */
+ROI3D_API size_t roi3d_refine_detections_workspace_bytes(int images, int rois_per_image, int max_instances);
+ROI3D_API int roi3d_refine_detections(const float *rois, const float *probs, const float *deltas, int images,
+                                      int rois_per_image, int num_classes, const float image_shape[3],
+                                      const float std_dev[6], float min_confidence, float nms_threshold,
+                                      int max_instances, float *detections, int *det_count,
+                                      void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Mask targets and the target files' wire format
+ * roi3d_mask_targets  replaces detection_targets_graph._get_masks, core/models.py:972-1005: tf.gather of the assigned
+ *                     ground-truth masks, cast to float32, CropAndResize3D (C = 1, trilinear, extrapolation 0) and
+ *                     tf.round, in one kernel.  masks [G,H,W,D] (the transposed layout of :973), mask_dtype
+ *                     ROI3D_MASK_F32 / ROI3D_MASK_U8; boxes [n,6]; assignment int32 [n] (NULL = identity, the
+ *                     box_ids = range(n) of :989).  targets float32 [n,mh,mw,md] and/or bits (the packed form below,
+ *                     4-byte aligned); either may be NULL, not both.
+ * roi3d_pack_f16 / roi3d_unpack_f16   ndarray.astype(float16) (round to nearest even) and back: the `rois_aligned`
+ *                     payload of the target files, core/models.py:3613.
+ * roi3d_pack_bits / roi3d_unpack_bits numpy.packbits((x > 0.5).reshape(-1)) (MSB first, zero padded) and
+ *                     numpy.unpackbits(...)[:n] as float32: the `mask_bits` / `tm_bits` payloads, :3585-3595.
+ * n counts ELEMENTS.  The npz container around the payloads stays on the host.
+ * ------------------------------------------------------------------------- */
+#define ROI3D_MASK_F32 0
+#define ROI3D_MASK_U8 1
+ROI3D_API int roi3d_mask_targets(const void *masks, int mask_dtype, int G, int H, int W, int D, const float *boxes,
+                                 const int *assignment, int n, int mh, int mw, int md, float *targets,
+                                 unsigned char *bits, roi3d_stream_t stream);
+ROI3D_API int roi3d_pack_f16(const float *x, long long n, void *half_out, roi3d_stream_t stream);
+ROI3D_API int roi3d_unpack_f16(const void *half_in, long long n, float *y, roi3d_stream_t stream);
+ROI3D_API int roi3d_pack_bits(const float *x, long long n, unsigned char *bits, roi3d_stream_t stream);
+ROI3D_API int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y, roi3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Tuning / introspection (not part of the reference surface).
  * roi3d_set_option: process-wide knobs used by the benchmarks and tests to
  * select a kernel variant; the defaults are the production choice.
- *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable
+ *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable, 3 = plane-staged fed by TMA bulk
+ *                       copies (bit-exact, slower at the row sizes of this path; opt-in)
  *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
  *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane kernels
  *   "nms_variant"       reserved

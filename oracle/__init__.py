@@ -237,3 +237,86 @@ def decode_proposals(anchors, deltas, std_dev, image_depth, index=None):
     out[:, 4] = np.maximum(out[:, 4], out[:, 1] + np.float32(1e-6))
     out[:, 5] = np.maximum(out[:, 5], out[:, 2] + min_dz)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# DetectionLayer and the target files: numpy restatements, fp32
+# ---------------------------------------------------------------------------------------------
+def refine_decode(rois, probs, deltas, image_shape, min_confidence, bbox_std_dev=(0.1, 0.1, 0.1, 0.2, 0.2, 0.2)):
+    """The per-ROI half of refine_detections_graph (core/models.py:1440-1488): pixel boxes after deltas + clip, the
+    class-1 score, and the mask of ROIs that pass the confidence and min-size filters."""
+    rois = np.asarray(rois, np.float32)
+    score = np.asarray(probs, np.float32)[:, 1]
+    d = np.asarray(deltas, np.float32)[:, 1, :] * np.asarray(bbox_std_dev, np.float32)[None, :]
+    dim = np.asarray(image_shape, np.float32)[:3]
+    scale = np.concatenate([dim, dim])
+    b = rois * scale[None, :]                                              # denorm_boxes_3d_graph, core/utils.py:401
+    half, lim = np.float32(0.5), np.float32(np.log(np.float32(62.5)))      # apply_box_deltas_3d_graph, :412-464
+    out = np.empty_like(b)
+    for a in range(3):
+        ln = b[:, a + 3] - b[:, a]
+        ctr = b[:, a] + half * ln
+        ds = np.clip(d[:, a + 3], -lim, lim)
+        ctr2 = ctr + d[:, a] * ln
+        ln2 = ln * np.exp(ds)
+        lo = ctr2 - half * ln2
+        out[:, a] = np.clip(lo, np.float32(0), dim[a])
+        out[:, a + 3] = np.clip(lo + ln2, np.float32(0), dim[a])
+    ok = (score >= np.float32(min_confidence)) & (out[:, 3] - out[:, 0] >= 1.0) & (out[:, 4] - out[:, 1] >= 1.0) & \
+        (out[:, 5] - out[:, 2] >= 0.5)
+    return out.astype(np.float32), score, ok
+
+
+def refine_detections(rois, probs, deltas, image_shape, min_confidence, nms_threshold,
+                      bbox_std_dev=(0.1, 0.1, 0.1, 0.2, 0.2, 0.2), max_instances=200, boxes_px=None):
+    """refine_detections_graph (core/models.py:1415-1524) for one image with the 3-D op as its NMS (row f3).
+    ``boxes_px`` overrides the decoded pixel boxes (tests pass the device's, whose expf may differ in the last ulp,
+    to compare the selection exactly)."""
+    px, score, ok = refine_decode(rois, probs, deltas, image_shape, min_confidence, bbox_std_dev)
+    if boxes_px is not None:
+        px = np.asarray(boxes_px, np.float32)
+    det = np.zeros((int(max_instances), 8), np.float32)
+    ix = np.nonzero(ok)[0]
+    if len(ix) == 0:
+        return det
+    sel = non_max_suppression_3d(px[ix], score[ix], int(max_instances), float(nms_threshold))
+    fb, fs = px[ix][sel], score[ix][sel]
+    order = np.argsort(-fs, kind="stable")                                 # tf.nn.top_k: descending, ties -> lower index
+    fb, fs = fb[order], fs[order]
+    dim = np.asarray(image_shape, np.float32)[:3]
+    scale = np.concatenate([dim, dim])
+    k = len(fs)
+    det[:k, :6] = np.clip(fb / scale[None, :], np.float32(0), np.float32(1))
+    det[:k, 6] = 1.0
+    det[:k, 7] = fs
+    return det
+
+
+def mask_targets(masks, boxes, assignment, mask_shape):
+    """detection_targets_graph._get_masks (core/models.py:972-1005): gather, cast, CropAndResize3D (C = 1), tf.round.
+    ``masks [G,H,W,D]`` any dtype; returns float32 ``[N,mh,mw,md]``."""
+    m = np.asarray(masks).astype(np.float32)[..., None]
+    n = len(boxes)
+    ids = np.arange(n, dtype=np.int32) if assignment is None else np.asarray(assignment, np.int32)
+    crops = crop_and_resize_3d(m, boxes, ids, mask_shape, "trilinear", 0.0)
+    return np.rint(crops[..., 0]).astype(np.float32)                       # tf.round = half to even
+
+
+def pack_f16(x):
+    """core/models.py:3613: ``ra.astype(np.float16)``."""
+    with np.errstate(over="ignore"):
+        return np.asarray(x, np.float32).astype(np.float16)
+
+
+def pack_bits(x):
+    """core/models.py:3585-3595 ``_bitpack``: ``(packed uint8, shape int32)``."""
+    a = np.asarray(x)
+    if a.dtype != np.uint8:
+        a = (a > 0.5).astype(np.uint8)
+    return np.packbits(a.reshape(-1)), np.array(a.shape, dtype=np.int32)
+
+
+def unpack_bits(bits, shape):
+    """The reader side: ``np.unpackbits(bits)[:prod(shape)].reshape(shape)`` as float32."""
+    n = int(np.prod(shape))
+    return np.unpackbits(np.asarray(bits, np.uint8))[:n].reshape(shape).astype(np.float32)

@@ -215,3 +215,50 @@ def test_synth_contract():
     assert lv.min() >= 2 and lv.max() <= 5
     b = roi3d_synth.rois(4, (128, 128, 128), 1)
     assert roi3d_synth.car_algorithmic_bytes(b, (1, 32, 32, 128, 256), (7, 7, 7)) > 4 * 343 * 1024
+
+
+# ---------------------------------------------------------------------------------------------
+# rows f3 / f4: the numpy restatements of DetectionLayer, mask targets and the target files' payloads
+# ---------------------------------------------------------------------------------------------
+def test_refine_detections_restatement_properties():
+    rng = np.random.default_rng(11)
+    R = 400
+    rois = roi3d_synth.nms_boxes(R, (128, 128, 64), seed=5)[0]
+    probs = rng.random((R, 2)).astype(np.float32)
+    deltas = (rng.standard_normal((R, 2, 6)) * 0.5).astype(np.float32)
+    shape = (128.0, 128.0, 64.0)
+    det = oracle.refine_detections(rois, probs, deltas, shape, 0.6, 0.3, max_instances=50)
+    k = int((det[:, 6] > 0).sum())
+    assert det.shape == (50, 8) and 0 < k <= 50 and not det[k:].any()
+    assert np.all(det[:k, 7] >= 0.6) and np.all(np.diff(det[:k, 7]) <= 0)
+    assert np.all((det[:k, :6] >= 0) & (det[:k, :6] <= 1))
+    # the kept boxes are mutually below the threshold under the op's own IoU, in pixel space
+    kept_px = det[:k, :6] * np.array(shape + shape, np.float32)
+    for i in range(min(k, 20)):
+        for j in range(i):
+            assert oracle.iou3d(kept_px, i, j) < 0.3 + 1e-4
+    # zero deltas, threshold 1: every ROI that passes the size filter comes back, as itself, in score order
+    px0, _, ok0 = oracle.refine_decode(rois, probs, np.zeros_like(deltas), shape, 0.0)
+    det0 = oracle.refine_detections(rois, probs, np.zeros_like(deltas), shape, 0.0, 1.0, max_instances=R)
+    order = np.argsort(-probs[:, 1], kind="stable")
+    order = order[ok0[order]]
+    assert np.array_equal(det0[: len(order), 7], probs[order, 1])
+    assert np.allclose(det0[: len(order), :6], np.clip(rois[order], 0, 1), atol=1e-6)
+    # nothing passes the confidence filter -> all zeros (the graph's _empty branch)
+    assert not oracle.refine_detections(rois, probs, deltas, shape, 2.0, 0.3, max_instances=7).any()
+
+
+def test_mask_targets_and_payload_restatements():
+    rng = np.random.default_rng(12)
+    masks = (rng.random((3, 8, 8, 8)) > 0.5)
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [0.25, 0.25, 0.25, 0.75, 0.75, 0.75]], np.float32)
+    out = oracle.mask_targets(masks, boxes, np.array([2, 0], np.int32), (8, 8, 8))
+    assert np.array_equal(out[0], masks[2].astype(np.float32))               # identity crop of a binary mask
+    assert set(np.unique(out)) <= {0.0, 1.0}
+    bits, shape = oracle.pack_bits(out)
+    assert bits.dtype == np.uint8 and len(bits) == out.size // 8 and tuple(shape) == out.shape
+    assert np.array_equal(oracle.unpack_bits(bits, shape), out)
+    x = np.array([0.5, 0.50001, 1.0, 0.0, 7.0, -1.0, 0.4, 0.6, 0.9], np.float32)
+    b, _ = oracle.pack_bits(x)
+    assert list(b) == [0b01101001, 0b10000000]                               # MSB first, zero padded
+    assert oracle.pack_f16(np.array([65520.0, 1e-8, 1.0009765625], np.float32)).tolist() == [np.inf, 0.0, 1.0009765625]
