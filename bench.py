@@ -364,6 +364,55 @@ def run_ours(args):
                 "ms": round(statistics.median(pl_ms), 4), "note": "top-k radix select + decode + NMS3D + gather/pad, no host sync"}
     del an, dlt, scr
 
+    # ---- rows f3 / f4: DetectionLayer, mask targets, target-file payloads -------------------
+    def timed(fn, reps=25, warm=5):
+        out = []
+        for it in range(reps + warm):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if it >= warm:
+                out.append(a.elapsed_time(b))
+        return statistics.median(out)
+
+    # cfg3 detection half: 2000 refined ROIs per image, 2 classes, DETECTION_MAX_INSTANCES keeps; batch 8 in one call
+    rng = np.random.default_rng(4242)
+    det_B, det_R, det_M = 8, 2000, 200
+    d_rois = torch.from_numpy(np.stack([roi3d_synth.nms_boxes(det_R, VOLUME, seed=500 + i)[0] for i in range(det_B)])).to(dev)
+    d_probs = torch.softmax(torch.from_numpy(rng.standard_normal((det_B, det_R, 2)).astype(np.float32) * 2), -1).to(dev)
+    d_dl = torch.from_numpy(rng.standard_normal((det_B, det_R, 2, 6)).astype(np.float32)).to(dev)
+    det_ms = timed(lambda: rb.refine_detections(d_rois, d_probs, d_dl, VOLUME, 0.5, 0.3, None, det_M))
+    det1_ms = timed(lambda: rb.refine_detections(d_rois[0], d_probs[0], d_dl[0], VOLUME, 0.5, 0.3, None, det_M))
+    _, det_cnt = rb.refine_detections(d_rois, d_probs, d_dl, VOLUME, 0.5, 0.3, None, det_M, return_counts=True)
+    detection = {"images": det_B, "rois_per_image": det_R, "max_instances": det_M, "ms_batch8": round(det_ms, 4),
+                 "ms_single_image": round(det1_ms, 4), "kept": [int(v) for v in det_cnt.cpu()],
+                 "note": "decode + filters folded into NMS3D candidates + gather/normalise/pad; 5 launches, no host sync"}
+    del d_rois, d_probs, d_dl
+    # mask targets: 128 positive ROIs x 28^3 from uint8 ground-truth masks of a 128^3 volume, rounded + bit-packed
+    mt_G, mt_n = 32, 128
+    gmask = (torch.rand((mt_G,) + tuple(VOLUME), device=dev) > 0.7).to(torch.uint8)
+    mt_boxes = torch.from_numpy(roi3d_synth.rois(mt_n, VOLUME, seed=9)).to(dev)
+    mt_assign = torch.randint(0, mt_G, (mt_n,), device=dev, dtype=torch.int32)
+    mt_ms = timed(lambda: rb.mask_targets(gmask, mt_boxes, mt_assign, (28, 28, 28), packed=True))
+    mask_t = {"rois": mt_n, "mask_shape": [28, 28, 28], "gt_masks": mt_G, "ms": round(mt_ms, 4),
+              "out_gbs": round(mt_n * 28 ** 3 * (4 + 0.125) / mt_ms / 1e6, 1)}
+    del gmask
+    # target-file payloads: rois_aligned of 1000 ROIs x 7^3 x 256 -> float16; a 1000 x 28^3 mask -> bits
+    ra = torch.randn((1000, 7, 7, 7, 256), device=dev)
+    tm = (torch.rand((1000, 28, 28, 28), device=dev) > 0.5).float()
+    f16_ms = timed(lambda: rb.pack_f16(ra))
+    h16 = rb.pack_f16(ra)
+    uf16_ms = timed(lambda: rb.unpack_f16(h16))
+    pb_ms = timed(lambda: rb.pack_bits(tm))
+    bits_t, _ = rb.pack_bits(tm)
+    ub_ms = timed(lambda: rb.unpack_bits(bits_t, tm.shape))
+    wire = {"pack_f16_gbs": round(ra.numel() * 6 / f16_ms / 1e6, 1), "unpack_f16_gbs": round(ra.numel() * 6 / uf16_ms / 1e6, 1),
+            "pack_bits_gbs": round(tm.numel() * 4.125 / pb_ms / 1e6, 1), "unpack_bits_gbs": round(tm.numel() * 4.125 / ub_ms / 1e6, 1),
+            "note": "algorithmic bytes (read + write) / event time, through the Python mirror (includes its allocation)"}
+    del ra, tm, h16, bits_t
+
     # ---- end to end through the public API with host buffers ---------------------------------------
     # Per step: every level's feature map is uploaded once (pinned host -> device), boxes / box indices / grads
     # go in as host buffers with each call, every crop and every grad image comes back to pinned host memory.
@@ -417,6 +466,9 @@ def run_ours(args):
         "nms3d": nms,
         "pyramid_fused": fused,
         "proposal_layer": proposal,
+        "detection_layer": detection,
+        "mask_targets": mask_t,
+        "target_file_payloads": wire,
         "ops": per_op,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
