@@ -231,8 +231,10 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
 //     earlier conflicting box of the chunk is decided removed; it is removed once one of them
 //     is decided kept) -- a few __ballot_sync rounds instead of 32 dependent steps;
 //   - the kept rows of the chunk are OR-ed into the lanes' words from the shared block.
-// At a super-chunk boundary all 32 warps OR the kept rows (global mask, coalesced row reads)
-// into the shared `removed` bitmap of the not-yet-visited words.
+// Suppression reaches later super-chunks lazily, one super-chunk ahead: while warp 0 resolves s, the other warps
+// OR the mask words of super-chunk s+1 over all rows kept BEFORE s (their positions are logged in `krows`); at the
+// boundary all 32 warps add the rows kept IN s.  Each (kept row, word) pair is read at most once, in batches of
+// independent loads, and never for columns the scan does not reach (it stops at max_out).
 // ---------------------------------------------------------------------------------
 constexpr int SC_THREADS = 1024;
 constexpr int SC_SB = 512;                 // boxes per super-chunk
@@ -259,23 +261,45 @@ __device__ __forceinline__ void sc_prefetch(unsigned *dst, float *vol, int *sidx
     }
 }
 
+// OR the mask words [w0, w0+16) of the kept rows krows[q0 .. q1) into dst[16].  Thread t of `nthreads` owns word
+// t % 16 of every (t / 16)-th row: 16 threads read one 64-byte row segment, the loads of a thread are independent
+// (accumulated in a register, 8 in flight), one shared atomic per thread at the end.
+__device__ __forceinline__ void sc_or_rows(unsigned *dst, const unsigned *__restrict__ mask, int pitch_words,
+                                           const int *krows, int q0, int q1, int w0, int nwords, int tid, int nthreads)
+{
+    const int w = tid & (SC_W - 1), g = tid / SC_W, ng = nthreads / SC_W;
+    if (g >= ng || w0 + w >= nwords) return;
+    const unsigned *col = mask + w0 + w;
+    unsigned acc = 0u;
+    int q = q0 + g;
+    for (; q + 7 * ng < q1; q += 8 * ng) {
+        unsigned m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m[u] = __ldg(col + (size_t)krows[q + u * ng] * pitch_words);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc |= m[u];
+    }
+    for (; q < q1; q += ng) acc |= __ldg(col + (size_t)krows[q] * pitch_words);
+    if (acc) atomicOr(dst + w, acc);
+}
+
 __global__ void __launch_bounds__(SC_THREADS)
 nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *__restrict__ sboxes,
                 const int *__restrict__ sorted_idx, const int *__restrict__ nvalid_p, int seg_stride,
-                int max_out, float thr, int *__restrict__ keep_idx, int *__restrict__ keep_count)
+                int max_out, float thr, int *__restrict__ krows, int *__restrict__ keep_idx, int *__restrict__ keep_count)
 {
     extern __shared__ unsigned s_dyn[];
-    unsigned *s_removed = s_dyn;                               // pitch_words words
-    unsigned *s_blk = s_dyn + pitch_words;                     // 2 x SC_SB x SC_P words
+    unsigned *s_blk = s_dyn;                                   // 2 x SC_SB x SC_P words
     float *s_vol = reinterpret_cast<float *>(s_blk + 2 * SC_SB * SC_P);   // 2 x SC_SB
     int *s_sidx = reinterpret_cast<int *>(s_vol + 2 * SC_SB);             // 2 x SC_SB
-    __shared__ int s_krows[SC_SB];                             // kept rows of the current super-chunk
-    __shared__ int s_nk, s_nsel, s_fill, s_done;
+    __shared__ unsigned s_rem[2][SC_W];                        // removed bits of the current / the next super-chunk
+    __shared__ int s_nsel, s_fill, s_done;
     {
         const size_t z = blockIdx.x;                                   // one CTA per segment
         mask += z * seg_stride * pitch_words;
         sboxes += z * seg_stride;
         sorted_idx += z * seg_stride;
+        krows += z * seg_stride;
         nvalid_p += z;
         keep_idx += z * max_out;
         keep_count += z;
@@ -284,27 +308,32 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (nvalid + 31) >> 5;
     const int nsuper = (nvalid + SC_SB - 1) / SC_SB;
-    for (int t = threadIdx.x; t < pitch_words; t += blockDim.x) s_removed[t] = 0u;
-    if (threadIdx.x == 0) { s_nsel = 0; s_fill = -1; s_done = 0; s_nk = 0; }
+    if (threadIdx.x < 2 * SC_W) s_rem[threadIdx.x / SC_W][threadIdx.x % SC_W] = 0u;
+    if (threadIdx.x == 0) { s_nsel = 0; s_fill = -1; s_done = 0; }
     sc_prefetch(s_blk, s_vol, s_sidx, mask, pitch_words, sboxes, sorted_idx, 0, nvalid, nwords, threadIdx.x, SC_THREADS);
     __syncthreads();
     const bool self_suppresses = (0.0f >= thr);                // thr == 0: even a zero-volume box suppresses itself
 
     for (int s = 0; s < nsuper; ++s) {
-        unsigned *blk = s_blk + (s & 1) * (SC_SB * SC_P);
-        const float *bvol = s_vol + (s & 1) * SC_SB;
-        const int *bsidx = s_sidx + (s & 1) * SC_SB;
+        const int cur = s & 1, nxt = cur ^ 1;
+        unsigned *blk = s_blk + cur * (SC_SB * SC_P);
+        const float *bvol = s_vol + cur * SC_SB;
+        const int *bsidx = s_sidx + cur * SC_SB;
+        const int k_before = s_nsel;                           // rows kept before this super-chunk: krows[0 .. k_before)
         if (warp != 0) {
-            // background: stage the diagonal block of the next super-chunk
+            // background: stage the diagonal block of the next super-chunk and OR the rows kept so far into ITS
+            // removed words -- suppression is propagated lazily, one super-chunk ahead, never to columns the scan
+            // may not reach
             if (s + 1 < nsuper) {
-                const int nb = (s + 1) & 1;
-                sc_prefetch(s_blk + nb * (SC_SB * SC_P), s_vol + nb * SC_SB, s_sidx + nb * SC_SB, mask, pitch_words,
+                sc_prefetch(s_blk + nxt * (SC_SB * SC_P), s_vol + nxt * SC_SB, s_sidx + nxt * SC_SB, mask, pitch_words,
                             sboxes, sorted_idx, s + 1, nvalid, nwords, threadIdx.x - 32, SC_THREADS - 32);
+                sc_or_rows(s_rem[nxt], mask, pitch_words, krows, 0, k_before, (s + 1) * SC_W, nwords,
+                           threadIdx.x - 32, SC_THREADS - 32);
             }
         } else {
-            int nsel = s_nsel, nk = 0, fill = -1;
+            int nsel = k_before, fill = -1;
             bool done = false;
-            unsigned rem = (lane < SC_W && s * SC_W + lane < nwords) ? s_removed[s * SC_W + lane] : 0xFFFFFFFFu;
+            unsigned rem = (lane < SC_W && s * SC_W + lane < nwords) ? s_rem[cur][lane] : 0xFFFFFFFFu;
             const unsigned lt = (1u << lane) - 1u;
             for (int c = 0; c < SC_W && !done; ++c) {
                 const int row = s * SC_SB + c * 32 + lane;
@@ -348,44 +377,52 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
                 if ((kept >> lane) & 1u) {
                     const int slot = __popc(kept & lt);
                     keep_idx[nsel + slot] = bsidx[c * 32 + lane];
-                    s_krows[nk + slot] = row;
+                    krows[nsel + slot] = row;
                 }
                 nsel += cnt;
-                nk += cnt;
-                // OR the kept rows into the super-chunk's removed words: lane b offers row b of the block,
-                // one warp OR-reduction per remaining word, lane w keeps word w
-                {
-                    const bool mine = (kept >> lane) & 1u;
+                // OR the kept rows into the super-chunk's removed words: lane b offers row b of the block (its 16
+                // words are read unconditionally: conflict-free, independent), one warp OR-reduction per word, lane w
+                // keeps word w.  Branch-free on purpose -- a guard per word made ptxas serialise the reductions.
+                // Words <= c are never read again, so they need none.
+                if (__popc(kept) > 8) {                        // warp-uniform
+                    const unsigned keepmask = ((kept >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
                     const unsigned *myrow = blk + (c * 32 + lane) * SC_P;
+                    unsigned v[SC_W];
 #pragma unroll
-                    for (int w = 1; w < SC_W; ++w) {
-                        if (w > c) {
-                            const unsigned v = __reduce_or_sync(0xffffffffu, mine ? myrow[w] : 0u);
-                            if (lane == w) rem |= v;
-                        }
+                    for (int w = 0; w < SC_W; ++w) v[w] = myrow[w] & keepmask;
+#pragma unroll
+                    for (int w = 0; w < SC_W; ++w) {
+                        const unsigned r = __reduce_or_sync(0xffffffffu, v[w]);
+                        rem |= (lane == w) ? r : 0u;
                     }
+                } else {
+                    // few kept rows: lane (h, w) = (lane >> 4, lane & 15) reads word w of every second kept row,
+                    // the two halves are combined with one shuffle
+                    const int w = lane & (SC_W - 1), half = lane >> 4;
+                    const unsigned *col = blk + (c * 32) * SC_P + w;
+                    unsigned k = kept, acc = 0u;
+                    while (k) {
+                        const int b0 = __ffs(k) - 1;
+                        k &= k - 1u;
+                        const int b1 = k ? __ffs(k) - 1 : b0;   // odd count: both halves read the same row
+                        k &= k - 1u;
+                        acc |= col[(half ? b1 : b0) * SC_P];
+                    }
+                    acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (lane < SC_W) rem |= acc;
                 }
             }
             if (lane == 0) {
                 s_nsel = nsel;
-                s_nk = nk;
                 s_done = done || nsel >= max_out;
                 s_fill = (fill >= 0) ? bsidx[fill - s * SC_SB] : -1;
             }
         }
-        __syncthreads();
-        if (s_done) break;
-        // boundary: every warp ORs kept rows into the not-yet-visited words
-        const int nk = s_nk, wfirst = (s + 1) * SC_W;
-        if (wfirst < nwords) {
-            for (int q = warp; q < nk; q += SC_THREADS / 32) {
-                const unsigned *mrow = mask + (size_t)s_krows[q] * pitch_words;
-                for (int w = wfirst + lane; w < nwords; w += 32) {
-                    const unsigned m = __ldg(mrow + w);
-                    if (m) atomicOr(&s_removed[w], m);
-                }
-            }
-        }
+        __syncthreads();                                       // also publishes warp 0's krows[] stores to the CTA
+        if (s_done || s + 1 >= nsuper) break;
+        // boundary: the rows kept in THIS super-chunk complete the next super-chunk's removed words
+        sc_or_rows(s_rem[nxt], mask, pitch_words, krows, k_before, s_nsel, (s + 1) * SC_W, nwords, threadIdx.x, SC_THREADS);
+        if (threadIdx.x < SC_W) s_rem[cur][threadIdx.x] = 0u;  // becomes the accumulator of super-chunk s + 2
         __syncthreads();
     }
     __syncthreads();
@@ -405,7 +442,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct NmsLayout {
     int pitch_words;
-    size_t off_sidx, off_sboxes, off_nvalid, off_mask, total;
+    size_t off_sidx, off_sboxes, off_nvalid, off_krows, off_mask, total;
 };
 
 static NmsLayout nms_layout(int n, int segments) {
@@ -417,6 +454,7 @@ static NmsLayout nms_layout(int n, int segments) {
     L.off_nvalid = off; off += align_up(sizeof(int) * S, 256);
     L.off_sidx = off;   off += align_up(sizeof(int) * S * n, 256);
     L.off_sboxes = off; off += align_up(sizeof(SBox) * S * n, 256);
+    L.off_krows = off;  off += align_up(sizeof(int) * S * n, 256);
     L.off_mask = off;   off += align_up(sizeof(unsigned) * S * n * L.pitch_words, 256);
     L.total = off;
     return L;
@@ -435,12 +473,12 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     }
     const NmsLayout L = nms_layout(n, S);
     if (ws == nullptr || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return ROI3D_EWORKSPACE;
-    if ((size_t)L.pitch_words * sizeof(unsigned) > 128 * 1024) return ROI3D_EUNSUPPORTED;   // > 1 M boxes
-    if (S > 65535) return ROI3D_EUNSUPPORTED;
+    if (S > 65535 || n > (1 << 20)) return ROI3D_EUNSUPPORTED;
     char *base = static_cast<char *>(ws);
     int *nvalid = reinterpret_cast<int *>(base + L.off_nvalid);
     int *sidx = reinterpret_cast<int *>(base + L.off_sidx);
     SBox *sboxes = reinterpret_cast<SBox *>(base + L.off_sboxes);
+    int *krows = reinterpret_cast<int *>(base + L.off_krows);
     unsigned *mask = reinterpret_cast<unsigned *>(base + L.off_mask);
     const NmsSeg seg{segments > 0 ? seg_offsets : nullptr, n, n};
 
@@ -450,9 +488,9 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
     nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, mask);
     ROI3D_LAUNCH_CHECK();
-    const size_t smem = ((size_t)L.pitch_words + 2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
+    const size_t smem = ((size_t)2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
     ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr,
+    nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, krows,
                                                     keep_idx, keep_count);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;

@@ -175,11 +175,32 @@ def run_ours(args):
         rb._lib.check(lib.roi3d_car3d_grad_image(ptr(op["d_grads"]), ptr(op["d_boxes"]), ptr(op["d_bidx"]), op["n"],
                                                  c[0], c[1], c[2], B, H, W, D, C, 0, ptr(op["d_gimg"]), stream()))
 
+    # The 8 forward nodes of a step are independent of each other, and so are the 8 grad-image nodes (each writes its
+    # own tensor; TF's executor schedules such nodes concurrently, SURVEY.md 8b "Threading / streams").  With
+    # --op-streams N > 1 the non-empty ops of each phase are spread over N streams that fork from and join into the
+    # main stream; the backward phase starts only after every forward has finished, as in training.
+    side = [torch.cuda.Stream(dev) for _ in range(max(args.op_streams, 1) - 1)]
+
+    def phase(fn):
+        if not side:
+            for op in ops:
+                fn(op)
+            return
+        cur = torch.cuda.current_stream()
+        lanes = [cur] + side
+        for s_ in side:
+            s_.wait_stream(cur)
+        busy = sorted((op for op in ops if op["n"]), key=lambda o: -o["fwd_bytes"])
+        idle = [op for op in ops if not op["n"]]
+        for i, op in enumerate(busy + idle):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                fn(op)
+        for s_ in side:
+            cur.wait_stream(s_)
+
     def step():
-        for op in ops:
-            fwd(op)
-        for op in ops:
-            bwd(op)
+        phase(fwd)
+        phase(bwd)
 
     def barrier():
         if world > 1:
@@ -456,7 +477,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "rois_per_step_per_gpu": total_rois, "l2": "inputs larger than L2 (feature maps + grads are %d MB per step; no explicit flush)" %
                    ((sum(t.numel() for t in images.values()) + sum(op["d_grads"].numel() for op in ops)) * 4 // 2 ** 20), "sharding": "one batch per GPU, no collective",
-                   "launch": ("CUDA graph replay of the %d C-ABI calls" % (2 * len(ops))) if graph is not None else "eager C-ABI calls"},
+                   "launch": (("CUDA graph replay of the %d C-ABI calls" % (2 * len(ops))) if graph is not None else "eager C-ABI calls") +
+                             ("; independent op nodes of each phase on %d streams (forward phase joins before the backward phase)" % args.op_streams
+                              if args.op_streams > 1 else "; one stream")},
         "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -615,6 +638,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--op-streams", type=int, default=1,
+                    help="streams the independent op nodes of each phase are spread over (1 = one stream, serial)")
     ap.add_argument("--no-graph", action="store_true", help="time eager C-ABI calls instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg")
