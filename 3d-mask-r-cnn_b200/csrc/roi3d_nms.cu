@@ -49,6 +49,13 @@ __device__ __forceinline__ int seg_size(const NmsSeg &g, int z) {
     return g.offsets ? __ldg(g.offsets + z + 1) - __ldg(g.offsets + z) : g.n;
 }
 
+// Scan state handed from the head phase to the tail phase (one per segment, in the workspace).
+struct ScanState {
+    int nsel;        // boxes selected so far (= entries of krows / keep_idx)
+    int done;        // the result is final: later phases exit at once
+    int pad0, pad1;
+};
+
 __device__ __forceinline__ unsigned score_key(float s) {
     // ascending unsigned key <=> descending score; invalid candidates -> 0xFFFFFFFF.
     // Candidate rule of the reference: score > -FLT_MAX (NaN fails it).  -0.0 == +0.0.
@@ -69,7 +76,8 @@ constexpr int RS_KTILE = 4096;      // keys staged per shared-memory tile
 
 __global__ void __launch_bounds__(RS_THREADS)
 nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, NmsSeg seg,
-                     int *__restrict__ sorted_idx, SBox *__restrict__ sboxes, int *__restrict__ nvalid_out)
+                     int *__restrict__ sorted_idx, SBox *__restrict__ sboxes, int *__restrict__ nvalid_out,
+                     ScanState *__restrict__ state)
 {
     const int z = blockIdx.y, n = seg_size(seg, z);
     if (blockIdx.x > 0 && blockIdx.x * RS_ITILE >= n) return;          // CTA-uniform; CTA 0 still publishes nvalid
@@ -134,7 +142,10 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
     }
     if (jq == 0) s_rank[il] = cnt;
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *nvalid_out = s_valid;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *nvalid_out = s_valid;
+        state[z] = ScanState{0, 0, 0, 0};
+    }
     if (threadIdx.x < RS_ITILE) {
         const int ii = blockIdx.x * RS_ITILE + threadIdx.x;
         if (ii < n) {
@@ -178,32 +189,37 @@ __device__ __forceinline__ bool iou_ge(const float4 a0, const float4 a1, const f
 
 __global__ void __launch_bounds__(MK_WARPS * 32)
 nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, float thr,
-                unsigned *__restrict__ mask)
+                int word_begin, int row_end, const ScanState *__restrict__ state, unsigned *__restrict__ mask)
 {
+    // The grid covers mask words [word_begin, ...) of rows [0, row_end): the head phase computes the top-left
+    // triangle (word_begin = 0, row_end = T), the tail phase everything right of it (word_begin = T / 32, all rows) --
+    // unless the head phase's scan already finished (state->done), which is the common case when max_out << n.
     __shared__ float4 s_rows[MK_ROWS * 2];
-    const int z = blockIdx.z, n = seg_size(seg, z);
+    const int z = blockIdx.z, n = min(seg_size(seg, z), row_end);
+    if (state != nullptr && state[z].done) return;                       // CTA-uniform
     const int i0 = blockIdx.y * MK_ROWS;
-    if (i0 >= n || blockIdx.x * MK_WARPS * 32 >= n) return;             // CTA-uniform
+    const int w0 = word_begin + blockIdx.x * MK_WARPS;
+    if (i0 >= n || w0 * 32 >= seg_size(seg, z)) return;                 // CTA-uniform
     sboxes += (size_t)z * seg.stride;
     mask += (size_t)z * seg.stride * pitch_words;
-    const int w0 = blockIdx.x * MK_WARPS;
     // only words that contain some column j >= i0 are ever read by the scan
     if ((w0 + MK_WARPS) * 32 <= i0) return;
+    const int ncol = seg_size(seg, z);
     const int rows = min(MK_ROWS, n - i0);
     for (int t = threadIdx.x; t < rows * 2; t += blockDim.x)
         s_rows[t] = __ldg(reinterpret_cast<const float4 *>(sboxes + i0) + t);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = w0 + warp;
-    if (w * 32 >= n || (w + 1) * 32 <= i0) return;
+    if (w * 32 >= ncol || (w + 1) * 32 <= i0) return;
     const int j = w * 32 + lane;
     // padding columns (j >= n): a far-away zero-size box never intersects anything
     float4 b0 = make_float4(3e38f, 3e38f, 3e38f, 3e38f), b1 = make_float4(3e38f, 3e38f, 0.f, 0.f);
-    if (j < n) {
+    if (j < ncol) {
         b0 = __ldg(reinterpret_cast<const float4 *>(sboxes + j));
         b1 = __ldg(reinterpret_cast<const float4 *>(sboxes + j) + 1);
     }
-    const bool pad_bit = (j >= n);
+    const bool pad_bit = (j >= ncol);
     for (int rb = 0; rb < rows; rb += 32) {
         // rows whose word lies entirely below the diagonal are never read
         if ((w + 1) * 32 <= i0 + rb) continue;
@@ -286,8 +302,12 @@ __device__ __forceinline__ void sc_or_rows(unsigned *dst, const unsigned *__rest
 __global__ void __launch_bounds__(SC_THREADS)
 nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *__restrict__ sboxes,
                 const int *__restrict__ sorted_idx, const int *__restrict__ nvalid_p, int seg_stride,
-                int max_out, float thr, int *__restrict__ krows, int *__restrict__ keep_idx, int *__restrict__ keep_count)
+                int max_out, float thr, int sb_begin, int sb_end, ScanState *__restrict__ state,
+                int *__restrict__ krows, int *__restrict__ keep_idx, int *__restrict__ keep_count)
 {
+    // Visits super-chunks [sb_begin, sb_end).  The head phase (sb_begin = 0) stops at sb_end = T / 512 and hands
+    // {nsel, krows, keep_idx} over through `state`; the tail phase resumes there -- or exits at once when the head
+    // phase already produced the final result.
     extern __shared__ unsigned s_dyn[];
     unsigned *s_blk = s_dyn;                                   // 2 x SC_SB x SC_P words
     float *s_vol = reinterpret_cast<float *>(s_blk + 2 * SC_SB * SC_P);   // 2 x SC_SB
@@ -303,18 +323,28 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         nvalid_p += z;
         keep_idx += z * max_out;
         keep_count += z;
+        state += z;
     }
+    if (state->done) return;                                   // CTA-uniform (written by the previous phase)
     const int nvalid = *nvalid_p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (nvalid + 31) >> 5;
     const int nsuper = (nvalid + SC_SB - 1) / SC_SB;
+    const int s_stop = min(sb_end, nsuper);
+    const int k_start = state->nsel;
     if (threadIdx.x < 2 * SC_W) s_rem[threadIdx.x / SC_W][threadIdx.x % SC_W] = 0u;
-    if (threadIdx.x == 0) { s_nsel = 0; s_fill = -1; s_done = 0; }
-    sc_prefetch(s_blk, s_vol, s_sidx, mask, pitch_words, sboxes, sorted_idx, 0, nvalid, nwords, threadIdx.x, SC_THREADS);
+    if (threadIdx.x == 0) { s_nsel = k_start; s_fill = -1; s_done = 0; }
+    if (sb_begin < s_stop)
+        sc_prefetch(s_blk + (sb_begin & 1) * (SC_SB * SC_P), s_vol + (sb_begin & 1) * SC_SB, s_sidx + (sb_begin & 1) * SC_SB,
+                    mask, pitch_words, sboxes, sorted_idx, sb_begin, nvalid, nwords, threadIdx.x, SC_THREADS);
     __syncthreads();
+    if (sb_begin > 0 && sb_begin < s_stop) {                   // resume: rebuild the first super-chunk's removed words
+        sc_or_rows(s_rem[sb_begin & 1], mask, pitch_words, krows, 0, k_start, sb_begin * SC_W, nwords, threadIdx.x, SC_THREADS);
+        __syncthreads();
+    }
     const bool self_suppresses = (0.0f >= thr);                // thr == 0: even a zero-volume box suppresses itself
 
-    for (int s = 0; s < nsuper; ++s) {
+    for (int s = sb_begin; s < s_stop; ++s) {
         const int cur = s & 1, nxt = cur ^ 1;
         unsigned *blk = s_blk + cur * (SC_SB * SC_P);
         const float *bvol = s_vol + cur * SC_SB;
@@ -324,7 +354,7 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
             // background: stage the diagonal block of the next super-chunk and OR the rows kept so far into ITS
             // removed words -- suppression is propagated lazily, one super-chunk ahead, never to columns the scan
             // may not reach
-            if (s + 1 < nsuper) {
+            if (s + 1 < s_stop) {
                 sc_prefetch(s_blk + nxt * (SC_SB * SC_P), s_vol + nxt * SC_SB, s_sidx + nxt * SC_SB, mask, pitch_words,
                             sboxes, sorted_idx, s + 1, nvalid, nwords, threadIdx.x - 32, SC_THREADS - 32);
                 sc_or_rows(s_rem[nxt], mask, pitch_words, krows, 0, k_before, (s + 1) * SC_W, nwords,
@@ -333,14 +363,24 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         } else {
             int nsel = k_before, fill = -1;
             bool done = false;
-            unsigned rem = (lane < SC_W && s * SC_W + lane < nwords) ? s_rem[cur][lane] : 0xFFFFFFFFu;
+            // removed bits inherited from earlier super-chunks: lane w holds word w
+            const unsigned rem_init = (lane < SC_W && s * SC_W + lane < nwords) ? s_rem[cur][lane] : 0xFFFFFFFFu;
             const unsigned lt = (1u << lane) - 1u;
-            for (int c = 0; c < SC_W && !done; ++c) {
+            // mine_or[w]: OR of word w over MY rows kept so far in this super-chunk (lane b owns row b of every
+            // chunk).  The chunk loop is fully unrolled so that the array lives in registers; the only warp
+            // reduction on the serial chain is the one that forms the current chunk's removed word.
+            unsigned mine_or[SC_W];
+#pragma unroll
+            for (int w = 0; w < SC_W; ++w) mine_or[w] = 0u;
+#pragma unroll
+            for (int c = 0; c < SC_W; ++c) {
+                if (done || s * SC_SB + c * 32 >= nvalid) continue;      // warp-uniform
                 const int row = s * SC_SB + c * 32 + lane;
-                if (s * SC_SB + c * 32 >= nvalid) break;
-                const unsigned rw = __shfl_sync(0xffffffffu, rem, c);
+                const unsigned *myrow = blk + (c * 32 + lane) * SC_P;
+                const unsigned d = myrow[c];                   // rows >= nvalid were staged as zeros
+                const unsigned nextw = (c + 1 < SC_W) ? myrow[c + 1] : 0u;   // needed right after this chunk: preload
                 const bool valid = row < nvalid;
-                const unsigned d = valid ? blk[(c * 32 + lane) * SC_P + c] : 0u;
+                const unsigned rw = __shfl_sync(0xffffffffu, rem_init, c) | __reduce_or_sync(0xffffffffu, mine_or[c]);
                 const unsigned sup = d & lt;                   // earlier boxes of this chunk that conflict with me
                 unsigned undecided = __ballot_sync(0xffffffffu, valid && !((rw >> lane) & 1u));
                 unsigned kept = 0u;
@@ -374,43 +414,16 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
                     }
                     done = true;
                 }
-                if ((kept >> lane) & 1u) {
+                const bool kept_me = (kept >> lane) & 1u;
+                if (c + 1 < SC_W) mine_or[c + 1] |= kept_me ? nextw : 0u;
+                if (kept_me) {
                     const int slot = __popc(kept & lt);
                     keep_idx[nsel + slot] = bsidx[c * 32 + lane];
                     krows[nsel + slot] = row;
+#pragma unroll
+                    for (int w = c + 2; w < SC_W; ++w) mine_or[w] |= myrow[w];   // off the serial chain
                 }
                 nsel += cnt;
-                // OR the kept rows into the super-chunk's removed words: lane b offers row b of the block (its 16
-                // words are read unconditionally: conflict-free, independent), one warp OR-reduction per word, lane w
-                // keeps word w.  Branch-free on purpose -- a guard per word made ptxas serialise the reductions.
-                // Words <= c are never read again, so they need none.
-                if (__popc(kept) > 8) {                        // warp-uniform
-                    const unsigned keepmask = ((kept >> lane) & 1u) ? 0xFFFFFFFFu : 0u;
-                    const unsigned *myrow = blk + (c * 32 + lane) * SC_P;
-                    unsigned v[SC_W];
-#pragma unroll
-                    for (int w = 0; w < SC_W; ++w) v[w] = myrow[w] & keepmask;
-#pragma unroll
-                    for (int w = 0; w < SC_W; ++w) {
-                        const unsigned r = __reduce_or_sync(0xffffffffu, v[w]);
-                        rem |= (lane == w) ? r : 0u;
-                    }
-                } else {
-                    // few kept rows: lane (h, w) = (lane >> 4, lane & 15) reads word w of every second kept row,
-                    // the two halves are combined with one shuffle
-                    const int w = lane & (SC_W - 1), half = lane >> 4;
-                    const unsigned *col = blk + (c * 32) * SC_P + w;
-                    unsigned k = kept, acc = 0u;
-                    while (k) {
-                        const int b0 = __ffs(k) - 1;
-                        k &= k - 1u;
-                        const int b1 = k ? __ffs(k) - 1 : b0;   // odd count: both halves read the same row
-                        k &= k - 1u;
-                        acc |= col[(half ? b1 : b0) * SC_P];
-                    }
-                    acc |= __shfl_xor_sync(0xffffffffu, acc, 16);
-                    if (lane < SC_W) rem |= acc;
-                }
             }
             if (lane == 0) {
                 s_nsel = nsel;
@@ -419,7 +432,7 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
             }
         }
         __syncthreads();                                       // also publishes warp 0's krows[] stores to the CTA
-        if (s_done || s + 1 >= nsuper) break;
+        if (s_done || s + 1 >= s_stop) break;
         // boundary: the rows kept in THIS super-chunk complete the next super-chunk's removed words
         sc_or_rows(s_rem[nxt], mask, pitch_words, krows, k_before, s_nsel, (s + 1) * SC_W, nwords, threadIdx.x, SC_THREADS);
         if (threadIdx.x < SC_W) s_rem[cur][threadIdx.x] = 0u;  // becomes the accumulator of super-chunk s + 2
@@ -427,12 +440,19 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
     }
     __syncthreads();
     int nsel = s_nsel;
+    if (!s_done && s_stop < nsuper) {                          // more super-chunks to visit: hand over to the tail phase
+        if (threadIdx.x == 0) state->nsel = nsel;
+        return;
+    }
     const int fill = s_fill;
     if (fill >= 0) {                                           // zero-volume quirk: repeat until max_out
         for (int t = nsel + threadIdx.x; t < max_out; t += blockDim.x) keep_idx[t] = fill;
         nsel = max_out;
     }
-    if (threadIdx.x == 0) *keep_count = nsel;
+    if (threadIdx.x == 0) {
+        *keep_count = nsel;
+        state->done = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -442,7 +462,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct NmsLayout {
     int pitch_words;
-    size_t off_sidx, off_sboxes, off_nvalid, off_krows, off_mask, total;
+    size_t off_sidx, off_sboxes, off_nvalid, off_state, off_krows, off_mask, total;
 };
 
 static NmsLayout nms_layout(int n, int segments) {
@@ -452,6 +472,7 @@ static NmsLayout nms_layout(int n, int segments) {
     L.pitch_words = (int)align_up((size_t)(words > 0 ? words : 1), 32);   // 128-byte rows
     size_t off = 0;
     L.off_nvalid = off; off += align_up(sizeof(int) * S, 256);
+    L.off_state = off;  off += align_up(sizeof(ScanState) * S, 256);
     L.off_sidx = off;   off += align_up(sizeof(int) * S * n, 256);
     L.off_sboxes = off; off += align_up(sizeof(SBox) * S * n, 256);
     L.off_krows = off;  off += align_up(sizeof(int) * S * n, 256);
@@ -482,17 +503,38 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     unsigned *mask = reinterpret_cast<unsigned *>(base + L.off_mask);
     const NmsSeg seg{segments > 0 ? seg_offsets : nullptr, n, n};
 
-    nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, scores, seg, sidx, sboxes, nvalid);
-    ROI3D_LAUNCH_CHECK();
-    const int words = (n + 31) / 32;
-    dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
-    nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, mask);
+    ScanState *state = reinterpret_cast<ScanState *>(base + L.off_state);
+    nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, scores, seg, sidx, sboxes, nvalid, state);
     ROI3D_LAUNCH_CHECK();
     const size_t smem = ((size_t)2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
     ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, krows,
-                                                    keep_idx, keep_count);
-    ROI3D_LAUNCH_CHECK();
+    // Head / tail split.  The scan stops as soon as max_out boxes are selected, i.e. after about max_out sorted boxes
+    // when few of them suppress each other -- far from n.  So the first T = max_out * 1.25 + 256 boxes (rounded up
+    // to whole super-chunks) get their own mask triangle and scan; the rest of the mask (the bulk of the n^2 / 2
+    // pairs) and the tail scan are launched behind it and return immediately when the head already finished.
+    // nms_variant 1 forces the single-phase schedule.
+    const int nsb = (n + SC_SB - 1) / SC_SB;
+    int head_sb = (int)(((long long)max_out + max_out / 4 + 256 + SC_SB - 1) / SC_SB);
+    if (option_value(OPT_NMS_VARIANT) == 1 || head_sb >= nsb) head_sb = nsb;
+    const int T = min(head_sb * SC_SB, n);
+    {
+        const int words = (T + 31) / 32;
+        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (T + MK_ROWS - 1) / MK_ROWS, S);
+        nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
+        ROI3D_LAUNCH_CHECK();
+        nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, 0, head_sb,
+                                                        state, krows, keep_idx, keep_count);
+        ROI3D_LAUNCH_CHECK();
+    }
+    if (head_sb < nsb) {
+        const int wb = T / 32, words = (n + 31) / 32 - wb;
+        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
+        nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, wb, n, state, mask);
+        ROI3D_LAUNCH_CHECK();
+        nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, head_sb, nsb,
+                                                        state, krows, keep_idx, keep_count);
+        ROI3D_LAUNCH_CHECK();
+    }
     return ROI3D_OK;
 }
 
