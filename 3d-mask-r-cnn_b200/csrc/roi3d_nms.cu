@@ -69,13 +69,25 @@ __device__ __forceinline__ unsigned score_key(float s) {
 // ---------------------------------------------------------------------------------
 // 1. rank sort + gather
 // ---------------------------------------------------------------------------------
-constexpr int RS_ITILE = 8;         // boxes ranked per CTA
-constexpr int RS_JSPLIT = 32;       // threads sharing one box's j-range
+constexpr int RS_ITILE = 16;        // boxes ranked per CTA
+constexpr int RS_JSPLIT = 16;       // threads sharing one box's j-range (lanes of different boxes read the same
+                                    // 16-byte key vectors: shared-memory broadcast)
 constexpr int RS_THREADS = RS_ITILE * RS_JSPLIT;
-constexpr int RS_KTILE = 4096;      // keys staged per shared-memory tile
+constexpr int RS_KTILE = 8192;      // keys staged per shared-memory tile (32 KB)
+
+// 1a. scores -> 32-bit sort keys, once (padded to whole 4-key vectors with the "not a candidate" key), so that every
+// rank-sort CTA stages them with independent 16-byte loads instead of converting all n scores again
+__global__ void __launch_bounds__(256)
+nms_keys_kernel(const float *__restrict__ scores, NmsSeg seg, int kstride, unsigned *__restrict__ keys)
+{
+    const int z = blockIdx.y, n = seg_size(seg, z);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((n + 3) & ~3)) return;
+    keys[(size_t)z * kstride + i] = (i < n) ? score_key(__ldg(scores + seg_begin(seg, z) + i)) : 0xFFFFFFFFu;
+}
 
 __global__ void __launch_bounds__(RS_THREADS)
-nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, NmsSeg seg,
+nms_rank_sort_kernel(const float *__restrict__ boxes, const unsigned *__restrict__ keys, int kstride, NmsSeg seg,
                      int *__restrict__ sorted_idx, SBox *__restrict__ sboxes, int *__restrict__ nvalid_out,
                      ScanState *__restrict__ state)
 {
@@ -84,7 +96,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
     {
         const int base = seg_begin(seg, z);
         boxes += (size_t)base * 6;
-        scores += base;
+        keys += (size_t)z * kstride;
         sorted_idx += (size_t)z * seg.stride;
         sboxes += (size_t)z * seg.stride;
         nvalid_out += z;
@@ -95,7 +107,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
     const int il = threadIdx.x / RS_JSPLIT;                   // box within the CTA's tile
     const int jq = threadIdx.x % RS_JSPLIT;                   // lane over the key tile
     const int i = blockIdx.x * RS_ITILE + il;
-    const unsigned ki = (i < n) ? score_key(__ldg(scores + i)) : 0xFFFFFFFFu;
+    const unsigned ki = (i < n) ? __ldg(keys + i) : 0xFFFFFFFFu;
     if (threadIdx.x < RS_ITILE) s_rank[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_valid = 0;
     int cnt = 0, nvalid = 0;
@@ -106,10 +118,12 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
     for (int j0 = 0; j0 < n; j0 += RS_KTILE) {
         __syncthreads();
         const int tile = min(RS_KTILE, n - j0);
-        for (int t = threadIdx.x; t < RS_KTILE; t += RS_THREADS) {
-            const unsigned k = (t < tile) ? score_key(__ldg(scores + j0 + t)) : 0xFFFFFFFFu;
-            s_keys[t] = k;
-            if (blockIdx.x == 0 && t < tile && k != 0xFFFFFFFFu) ++nvalid;
+        const uint4 *src = reinterpret_cast<const uint4 *>(keys + j0);
+        for (int t = threadIdx.x; t < (tile + 3) / 4; t += RS_THREADS) {
+            const uint4 k4 = __ldg(src + t);
+            reinterpret_cast<uint4 *>(s_keys)[t] = k4;
+            if (blockIdx.x == 0)
+                nvalid += (k4.x != 0xFFFFFFFFu) + (k4.y != 0xFFFFFFFFu) + (k4.z != 0xFFFFFFFFu) + (k4.w != 0xFFFFFFFFu);
         }
         __syncthreads();
         const int tile4 = (tile + 3) & ~3;
@@ -132,13 +146,13 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
             cnt += (k4.x < ki) + (k4.y < ki) + (k4.z < ki) + (k4.w < ki);
         }
     }
-    // reduce the RS_JSPLIT partial counts of each box (RS_JSPLIT == warp size)
+    // reduce the RS_JSPLIT partial counts of each box (its lanes are adjacent within a warp)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    for (int o = RS_JSPLIT / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (blockIdx.x == 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-        if (jq == 0 && nvalid) atomicAdd(&s_valid, nvalid);
+        if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd(&s_valid, nvalid);
     }
     if (jq == 0) s_rank[il] = cnt;
     __syncthreads();
@@ -169,7 +183,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
 // ---------------------------------------------------------------------------------
 // 2. pairwise IoU bitmask
 // ---------------------------------------------------------------------------------
-constexpr int MK_ROWS = 128;        // row boxes staged per CTA
+constexpr int MK_ROWS = 128;        // row boxes staged per CTA (tail phase; the small head phase uses 32 for more CTAs)
 constexpr int MK_WARPS = 8;         // mask words (32 columns each) per CTA
 
 // IOU<float> (NMS.so@0xb500) on canonical boxes: same operations, same order.  The reference's
@@ -187,6 +201,7 @@ __device__ __forceinline__ bool iou_ge(const float4 a0, const float4 a1, const f
     return iou >= thr;
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(MK_WARPS * 32)
 nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, float thr,
                 int word_begin, int row_end, const ScanState *__restrict__ state, unsigned *__restrict__ mask)
@@ -194,10 +209,10 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
     // The grid covers mask words [word_begin, ...) of rows [0, row_end): the head phase computes the top-left
     // triangle (word_begin = 0, row_end = T), the tail phase everything right of it (word_begin = T / 32, all rows) --
     // unless the head phase's scan already finished (state->done), which is the common case when max_out << n.
-    __shared__ float4 s_rows[MK_ROWS * 2];
+    __shared__ float4 s_rows[ROWS * 2];
     const int z = blockIdx.z, n = min(seg_size(seg, z), row_end);
     if (state != nullptr && state[z].done) return;                       // CTA-uniform
-    const int i0 = blockIdx.y * MK_ROWS;
+    const int i0 = blockIdx.y * ROWS;
     const int w0 = word_begin + blockIdx.x * MK_WARPS;
     if (i0 >= n || w0 * 32 >= seg_size(seg, z)) return;                 // CTA-uniform
     sboxes += (size_t)z * seg.stride;
@@ -205,7 +220,7 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
     // only words that contain some column j >= i0 are ever read by the scan
     if ((w0 + MK_WARPS) * 32 <= i0) return;
     const int ncol = seg_size(seg, z);
-    const int rows = min(MK_ROWS, n - i0);
+    const int rows = min(ROWS, n - i0);
     for (int t = threadIdx.x; t < rows * 2; t += blockDim.x)
         s_rows[t] = __ldg(reinterpret_cast<const float4 *>(sboxes + i0) + t);
     __syncthreads();
@@ -462,7 +477,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct NmsLayout {
     int pitch_words;
-    size_t off_sidx, off_sboxes, off_nvalid, off_state, off_krows, off_mask, total;
+    int kstride;
+    size_t off_sidx, off_sboxes, off_nvalid, off_state, off_krows, off_keys, off_mask, total;
 };
 
 static NmsLayout nms_layout(int n, int segments) {
@@ -476,6 +492,8 @@ static NmsLayout nms_layout(int n, int segments) {
     L.off_sidx = off;   off += align_up(sizeof(int) * S * n, 256);
     L.off_sboxes = off; off += align_up(sizeof(SBox) * S * n, 256);
     L.off_krows = off;  off += align_up(sizeof(int) * S * n, 256);
+    L.kstride = (int)align_up((size_t)n, 4);
+    L.off_keys = off;   off += align_up(sizeof(unsigned) * S * L.kstride, 256);
     L.off_mask = off;   off += align_up(sizeof(unsigned) * S * n * L.pitch_words, 256);
     L.total = off;
     return L;
@@ -504,7 +522,10 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     const NmsSeg seg{segments > 0 ? seg_offsets : nullptr, n, n};
 
     ScanState *state = reinterpret_cast<ScanState *>(base + L.off_state);
-    nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, scores, seg, sidx, sboxes, nvalid, state);
+    unsigned *keys = reinterpret_cast<unsigned *>(base + L.off_keys);
+    nms_keys_kernel<<<dim3((L.kstride + 255) / 256, S), 256, 0, stream>>>(scores, seg, L.kstride, keys);
+    ROI3D_LAUNCH_CHECK();
+    nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, keys, L.kstride, seg, sidx, sboxes, nvalid, state);
     ROI3D_LAUNCH_CHECK();
     const size_t smem = ((size_t)2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
     ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -519,8 +540,12 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     const int T = min(head_sb * SC_SB, n);
     {
         const int words = (T + 31) / 32;
-        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (T + MK_ROWS - 1) / MK_ROWS, S);
-        nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
+        const int hrows = (head_sb < nsb) ? 32 : MK_ROWS;      // a small head triangle needs more, smaller CTAs
+        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (T + hrows - 1) / hrows, S);
+        if (hrows == 32)
+            nms_mask_kernel<32><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
+        else
+            nms_mask_kernel<MK_ROWS><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
         ROI3D_LAUNCH_CHECK();
         nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, 0, head_sb,
                                                         state, krows, keep_idx, keep_count);
@@ -529,7 +554,7 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     if (head_sb < nsb) {
         const int wb = T / 32, words = (n + 31) / 32 - wb;
         dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
-        nms_mask_kernel<<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, wb, n, state, mask);
+        nms_mask_kernel<MK_ROWS><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, wb, n, state, mask);
         ROI3D_LAUNCH_CHECK();
         nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, head_sb, nsb,
                                                         state, krows, keep_idx, keep_count);
