@@ -50,10 +50,11 @@ __device__ __forceinline__ int seg_size(const NmsSeg &g, int z) {
 }
 
 // Scan state handed from the head phase to the tail phase (one per segment, in the workspace).
-struct ScanState {
+struct __align__(16) ScanState {
     int nsel;        // boxes selected so far (= entries of krows / keep_idx)
     int done;        // the result is final: later phases exit at once
-    int pad0, pad1;
+    int nvalid;      // candidates (score > -FLT_MAX), published by the rank sort: one 16-byte load gets all three
+    int pad;
 };
 
 __device__ __forceinline__ unsigned score_key(float s) {
@@ -158,7 +159,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const unsigned *__restrict
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *nvalid_out = s_valid;
-        state[z] = ScanState{0, 0, 0, 0};
+        state[z] = ScanState{0, 0, s_valid, 0};
     }
     if (threadIdx.x < RS_ITILE) {
         const int ii = blockIdx.x * RS_ITILE + threadIdx.x;
@@ -340,13 +341,14 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         keep_count += z;
         state += z;
     }
-    if (state->done) return;                                   // CTA-uniform (written by the previous phase)
-    const int nvalid = *nvalid_p;
+    const int4 st0 = *reinterpret_cast<const int4 *>(state);   // {nsel, done, nvalid, -}
+    if (st0.y) return;                                         // CTA-uniform (written by the previous phase)
+    const int nvalid = st0.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (nvalid + 31) >> 5;
     const int nsuper = (nvalid + SC_SB - 1) / SC_SB;
     const int s_stop = min(sb_end, nsuper);
-    const int k_start = state->nsel;
+    const int k_start = st0.x;
     if (threadIdx.x < 2 * SC_W) s_rem[threadIdx.x / SC_W][threadIdx.x % SC_W] = 0u;
     if (threadIdx.x == 0) { s_nsel = k_start; s_fill = -1; s_done = 0; }
     if (sb_begin < s_stop)
@@ -378,15 +380,19 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         } else {
             int nsel = k_before, fill = -1;
             bool done = false;
-            // removed bits inherited from earlier super-chunks: lane w holds word w
-            const unsigned rem_init = (lane < SC_W && s * SC_W + lane < nwords) ? s_rem[cur][lane] : 0xFFFFFFFFu;
             const unsigned lt = (1u << lane) - 1u;
             // mine_or[w]: OR of word w over MY rows kept so far in this super-chunk (lane b owns row b of every
-            // chunk).  The chunk loop is fully unrolled so that the array lives in registers; the only warp
-            // reduction on the serial chain is the one that forms the current chunk's removed word.
+            // chunk), seeded with the removed bits inherited from earlier super-chunks.  The chunk loop is fully
+            // unrolled so that the array lives in registers; the only warp reduction on the serial chain is the one
+            // that forms the current chunk's removed word.
             unsigned mine_or[SC_W];
+            unsigned degen_lanes[SC_W];                        // zero-volume boxes per chunk (independent of the chain)
 #pragma unroll
-            for (int w = 0; w < SC_W; ++w) mine_or[w] = 0u;
+            for (int w = 0; w < SC_W; ++w) {
+                mine_or[w] = (lane == 0) ? ((s * SC_W + w < nwords) ? s_rem[cur][w] : 0xFFFFFFFFu) : 0u;
+                const bool dg = (s * SC_SB + w * 32 + lane < nvalid) && !(bvol[w * 32 + lane] > 0.0f) && !self_suppresses;
+                degen_lanes[w] = __ballot_sync(0xffffffffu, dg);
+            }
 #pragma unroll
             for (int c = 0; c < SC_W; ++c) {
                 if (done || s * SC_SB + c * 32 >= nvalid) continue;      // warp-uniform
@@ -395,23 +401,23 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
                 const unsigned d = myrow[c];                   // rows >= nvalid were staged as zeros
                 const unsigned nextw = (c + 1 < SC_W) ? myrow[c + 1] : 0u;   // needed right after this chunk: preload
                 const bool valid = row < nvalid;
-                const unsigned rw = __shfl_sync(0xffffffffu, rem_init, c) | __reduce_or_sync(0xffffffffu, mine_or[c]);
+                const unsigned rw = __reduce_or_sync(0xffffffffu, mine_or[c]);
                 const unsigned sup = d & lt;                   // earlier boxes of this chunk that conflict with me
                 unsigned undecided = __ballot_sync(0xffffffffu, valid && !((rw >> lane) & 1u));
                 unsigned kept = 0u;
+                // parallel greedy rule: a box is kept once no earlier conflicting box of the chunk is still
+                // undecided or kept; it is dropped as soon as one of them is kept.  One ballot when nothing conflicts.
                 while (undecided) {
                     const bool me = (undecided >> lane) & 1u;
-                    const bool drop = me && (sup & kept);
-                    const bool keep = me && !drop && !(sup & undecided);
+                    const bool keep = me && !(sup & (kept | undecided));
                     const unsigned nkp = __ballot_sync(0xffffffffu, keep);
-                    const unsigned ndr = __ballot_sync(0xffffffffu, drop);
                     kept |= nkp;
-                    undecided &= ~(nkp | ndr);
+                    if (!(undecided & ~nkp)) break;
+                    undecided = __ballot_sync(0xffffffffu, me && !keep && !(sup & kept));
                 }
                 // zero-volume quirk (NMS.so@0xdc55): a selected box whose self-IoU is 0 is selected again
                 // until max_out; everything after it is never reached
-                const bool degenerate = valid && !(bvol[c * 32 + lane] > 0.0f) && !self_suppresses;
-                const unsigned degen = __ballot_sync(0xffffffffu, degenerate) & kept;
+                const unsigned degen = degen_lanes[c] & kept;
                 if (degen) {
                     const int bq = __ffs(degen) - 1;
                     kept &= (2u << bq) - 1u;

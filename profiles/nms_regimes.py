@@ -33,6 +33,27 @@ for name, n, mo, thr, kw in cases:
         torch.cuda.synchronize()
         if it >= 10:
             ms.append(a.elapsed_time(e))
+    # the same call captured once in a CUDA graph (it is stream-ordered and allocation-free) and replayed
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rb._lib.check(lib.roi3d_nms3d(db.data_ptr(), ds.data_ptr(), n, mo, thr, keep.data_ptr(), cnt.data_ptr(),
+                                      ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream))
+    gms = []
+    for it in range(40):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        if it >= 10:
+            gms.append(a.elapsed_time(e))
+    import time
+    t0 = time.perf_counter()
+    for _ in range(200):
+        rb._lib.check(lib.roi3d_nms3d(db.data_ptr(), ds.data_ptr(), n, mo, thr, keep.data_ptr(), cnt.data_ptr(),
+                                      ws.data_ptr(), wsb, torch.cuda.current_stream().cuda_stream))
+    host_us = (time.perf_counter() - t0) / 200 * 1e6
+    torch.cuda.synchronize()
     k = int(cnt.item())
     order = np.argsort(-s, kind="stable")
     rank = np.empty(n, np.int64); rank[order] = np.arange(n)
@@ -40,4 +61,5 @@ for name, n, mo, thr, kw in cases:
     depth = int(rank[kept[-1]]) + 1 if k else 0
     if k < mo:
         depth = n
-    print("%-44s kept %5d  scan depth %6d  %.4f ms" % (name, k, depth, statistics.median(ms)), flush=True)
+    print("%-44s kept %5d  scan depth %6d  eager %.4f ms  graph %.4f ms  host enqueue %.1f us" %
+          (name, k, depth, statistics.median(ms), statistics.median(gms), host_us), flush=True)
