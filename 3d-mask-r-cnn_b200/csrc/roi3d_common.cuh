@@ -16,7 +16,7 @@ namespace roi3d {
 extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
-enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_COUNT };
+enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_COUNT };
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--max-gb", type=float, default=24.0)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--nms-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = rb._lib.load()
@@ -50,7 +51,7 @@ def main():
     print("| layout | C | pool | ROIs | fwd ms | fwd GB/s | fwd % | bwd ms | bwd GB/s | bwd % |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     rois_list = [64, 512, 4096] if args.quick else [64, 128, 256, 512, 1024, 2048, 4096, 8192]
-    for iso in (False, True):
+    for iso in (() if args.nms_only else (False, True)):
         for C in (64, 128, 256):
             shape = roi3d_synth.level_shape(vol, 2, batch=1, channels=C, isotropic=iso)
             torch.manual_seed(C)

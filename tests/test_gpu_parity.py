@@ -615,3 +615,36 @@ def test_nms_head_tail_schedule(rb, cuda_device, n, max_out, thr, kw):
     b2[pos, 3:] = b2[pos, :3]
     assert np.array_equal(run_nms(rb, cuda_device, b2, scores, max_out, thr),
                           oracle.non_max_suppression_3d(b2, scores, max_out, thr))
+
+
+@pytest.mark.parametrize("n,max_out,dist", [
+    (1, 1, "uniform"), (100, 50, "uniform"), (6000, 1000, "uniform"), (20000, 2000, "uniform"), (50000, 3000, "uniform"),
+    (5000, 5000, "constant"), (6000, 700, "peaked"), (6000, 6000, "wide"), (4097, 300, "ties"),
+])
+def test_nms_bucketed_sort(rb, cuda_device, n, max_out, dist):
+    """The bucketed sort (large n) orders exactly like the rank-by-counting sort: same NMS result for uniform scores,
+    constant scores (one bucket), scores crowded near 1, scores outside [0, 1] with NaN / -inf / -FLT_MAX non-candidates,
+    and heavy ties."""
+    boxes, scores = roi3d_synth.nms_boxes(n, (128, 128, 128), seed=31 + n)
+    rng = np.random.default_rng(n)
+    if dist == "constant":
+        scores[:] = 0.5
+    elif dist == "peaked":
+        scores = (1.0 - rng.random(n) ** 6 * 1e-3).astype(np.float32)
+    elif dist == "wide":
+        scores = (rng.standard_normal(n) * 3).astype(np.float32)
+        scores[::97] = np.nan
+        scores[5::101] = -np.inf
+        scores[7::103] = -np.finfo(np.float32).max
+        scores[9::107] = np.inf
+        scores[11::109] = -0.0
+        scores[13::113] = 0.0
+    elif dist == "ties":
+        scores = (rng.integers(0, 12, n) / 11.0).astype(np.float32)
+    ref = oracle.non_max_suppression_3d(boxes, scores, max_out, 0.5)
+    try:
+        for variant in (2, 1):
+            rb.custom_op.set_option("nms_sort_variant", variant)
+            assert np.array_equal(run_nms(rb, cuda_device, boxes, scores, max_out, 0.5), ref), variant
+    finally:
+        rb.custom_op.set_option("nms_sort_variant", 0)
