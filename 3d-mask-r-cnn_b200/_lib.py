@@ -32,7 +32,7 @@ EXPORTS = [
     "roi3d_version", "roi3d_strerror", "roi3d_last_cuda_error",
     "roi3d_nms3d_workspace_bytes", "roi3d_nms3d", "roi3d_nms3d_batched_workspace_bytes", "roi3d_nms3d_batched",
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
-    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
+    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_fwd_f16", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
     "roi3d_topk_workspace_bytes", "roi3d_topk", "roi3d_gather_pad_boxes",
     "roi3d_refine_detections_workspace_bytes", "roi3d_refine_detections", "roi3d_mask_targets",
     "roi3d_pack_f16", "roi3d_unpack_f16", "roi3d_pack_bits", "roi3d_unpack_bits",
@@ -99,6 +99,8 @@ def _declare(lib):
     lib.roi3d_car3d_grad_boxes.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, i, i, i, vp, vp]
     lib.roi3d_pyramid_roi_align_fwd.restype = i
     lib.roi3d_pyramid_roi_align_fwd.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp]
+    lib.roi3d_pyramid_roi_align_fwd_f16.restype = i
+    lib.roi3d_pyramid_roi_align_fwd_f16.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp]
     lib.roi3d_pyramid_roi_align_grad.restype = i
     lib.roi3d_pyramid_roi_align_grad.argtypes = [vp, vp, vp, i, i, vp, i, vp, i, i, i, vp]
     lib.roi3d_overlaps3d.restype = i

@@ -273,9 +273,9 @@ static int pyramid_check(const int level_shapes[4][3], int B, int C, const float
     return ROI3D_OK;
 }
 
-int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
-                                const float *boxes, int rois_per_image, const float image_shape[3],
-                                int ph, int pw, int pd, float *pooled, roi3d_stream_t stream)
+static int pyramid_fwd_any(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                           const float *boxes, int rois_per_image, const float image_shape[3],
+                           int ph, int pw, int pd, void *pooled, bool half_out, roi3d_stream_t stream)
 {
     const int rc = pyramid_check(level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd);
     if (rc != ROI3D_OK) return rc;
@@ -286,9 +286,23 @@ int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int le
         if (!feature_maps[l] || (reinterpret_cast<uintptr_t>(feature_maps[l]) & 15)) return ROI3D_EINVAL;
         H[l] = level_shapes[l][0]; W[l] = level_shapes[l][1]; D[l] = level_shapes[l][2];
     }
-    if (reinterpret_cast<uintptr_t>(pooled) & 15) return ROI3D_EINVAL;
+    if (reinterpret_cast<uintptr_t>(pooled) & (half_out ? 7 : 15)) return ROI3D_EINVAL;
     return launch_pyramid_fwd(feature_maps, H, W, D, B, C, boxes, rois_per_image, image_shape[0], image_shape[1],
-                              image_shape[2], ph, pw, pd, pooled, static_cast<cudaStream_t>(stream));
+                              image_shape[2], ph, pw, pd, pooled, half_out, static_cast<cudaStream_t>(stream));
+}
+
+int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                const float *boxes, int rois_per_image, const float image_shape[3],
+                                int ph, int pw, int pd, float *pooled, roi3d_stream_t stream)
+{
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled, false, stream);
+}
+
+int roi3d_pyramid_roi_align_fwd_f16(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                    const float *boxes, int rois_per_image, const float image_shape[3],
+                                    int ph, int pw, int pd, void *pooled_f16, roi3d_stream_t stream)
+{
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled_f16, true, stream);
 }
 
 int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], const int level_shapes[4][3], int B, int C,

@@ -26,6 +26,7 @@
 // sum over per-axis contribution lists (deterministic order, no shared-memory atomics)
 // and issues two vector REDs (floor z, ceil z) instead of 8 per grads element.
 #include "roi3d_common.cuh"
+#include <type_traits>
 
 namespace roi3d {
 
@@ -188,12 +189,13 @@ __device__ __forceinline__ float4 sel4(bool bad, const float4 a, const float4 b)
 // ---------------------------------------------------------------------------------
 // forward.  V = float4 channel groups per thread (the chunk is cl * V * 4 channels).
 // ---------------------------------------------------------------------------------
-template <int V, bool PYR>
+template <int V, bool PYR, bool HALF = false>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                        const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
-                       float *__restrict__ crops, const PyrParams P)
+                       void *__restrict__ crops, const PyrParams P)
 {
+    using OutT = typename std::conditional<HALF, __half, float>::type;    // HALF: the target files' float16 payload
     constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
@@ -239,7 +241,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
     const float *img = image + (long long)bimg * g.H * sH + c4 * 4;
-    float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
+    OutT *crop = static_cast<OutT *>(crops) + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float4 ext4 = make_float4(ext, ext, ext, ext);
     const float z1 = S.box[2], z2 = S.box[5];
     const float zscale = axis_scale(z1, z2, g.D, g.pd);
@@ -280,7 +282,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
 
         for (int k = k0; k < k1; ++k) {
             const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
-            float *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
+            OutT *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
             if (axis_invalid(in_z, g.D) || nvox == 0) {       // uniform: every output of this (tile, k) extrapolates
                 for (int idx = slot; idx < nout; idx += vs, o += ostride) {
 #pragma unroll
@@ -757,7 +759,7 @@ static int pick_ksplits(const CarGeom &g, int chunks) {
 }
 
 static int launch_fwd_plane_impl(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
-                                 float ext, float *crops, const PyrParams *pyr, cudaStream_t stream)
+                                 float ext, void *crops, const PyrParams *pyr, cudaStream_t stream, bool half_out = false)
 {
     PlaneLaunch L;
     int V;
@@ -776,7 +778,9 @@ static int launch_fwd_plane_impl(const float *image, const float *boxes, const i
     }
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
-    auto kern = pyr ? ((V == 2) ? car3d_fwd_plane_kernel<2, true> : car3d_fwd_plane_kernel<1, true>)
+    if (half_out && !pyr) return ROI3D_EUNSUPPORTED;           // float16 output exists for the fused pyramid forward only
+    auto kern = half_out ? ((V == 2) ? car3d_fwd_plane_kernel<2, true, true> : car3d_fwd_plane_kernel<1, true, true>)
+              : pyr ? ((V == 2) ? car3d_fwd_plane_kernel<2, true> : car3d_fwd_plane_kernel<1, true>)
                     : ((V == 2) ? car3d_fwd_plane_kernel<2, false> : car3d_fwd_plane_kernel<1, false>);
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -858,7 +862,7 @@ int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const 
 // ---- fused PyramidROIAlign entry points (geometry g: B, C, n = B * R, crop; H/W/D = the largest level, for sizing) ----
 int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
                        const float *boxes, int rois_per_image, float imH, float imW, float imD,
-                       int ph, int pw, int pd, float *crops, cudaStream_t stream)
+                       int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream)
 {
     PyrParams P;
     for (int l = 0; l < 4; ++l) { P.image[l] = images[l]; P.H[l] = H[l]; P.W[l] = W[l]; P.D[l] = D[l]; }
@@ -866,7 +870,7 @@ int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W
     int wmax = 1;
     for (int l = 0; l < 4; ++l) wmax = max(wmax, W[l]);
     const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
-    return launch_fwd_plane_impl(nullptr, boxes, nullptr, g, 0.0f, crops, &P, stream);
+    return launch_fwd_plane_impl(nullptr, boxes, nullptr, g, 0.0f, crops, &P, stream, half_out);
 }
 
 int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],

@@ -7,6 +7,7 @@
 // FMAs nor reassociate them.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/roi3d.h"
 
@@ -66,6 +67,12 @@ __device__ __forceinline__ float4 ldg4(const float *p) {
 // streaming (evict-first) 128-bit store: crops / grads are written once and not re-read here
 __device__ __forceinline__ void st_stream4(float *p, const float4 v) {
     __stcs(reinterpret_cast<float4 *>(p), v);
+}
+// float16 flavour: round to nearest even (ndarray.astype(float16) for finite inputs), one 8-byte streaming store
+__device__ __forceinline__ void st_stream4(__half *p, const float4 v) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(*reinterpret_cast<const unsigned *>(&lo)),
+                 "r"(*reinterpret_cast<const unsigned *>(&hi)) : "memory");
 }
 // vectorised fire-and-forget global reduction (sm_90+): one 16-byte RED per 4 channels
 __device__ __forceinline__ void red_add4(float *p, const float4 v) {
@@ -153,7 +160,7 @@ int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const 
                                   float *grad_image, cudaStream_t stream);
 int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
                        const float *boxes, int rois_per_image, float imH, float imW, float imD,
-                       int ph, int pw, int pd, float *crops, cudaStream_t stream);
+                       int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream);
 int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],
                         int B, int C, const float *boxes, int rois_per_image, float imH, float imW, float imD,
                         int ph, int pw, int pd, cudaStream_t stream);

@@ -482,19 +482,32 @@ class PyramidROIAlign3DFunction(torch.autograd.Function):
         return (None, None, None) + tuple(gms)
 
 
-def pyramid_roi_align_3d(boxes, image_shape, feature_maps, pool_shape):
+def pyramid_roi_align_3d(boxes, image_shape, feature_maps, pool_shape, out_dtype=torch.float32):
     """Fused ``PyramidROIAlign(pool_shape)([boxes, image_meta, P2, P3, P4, P5])`` (core/models.py:604-685).
 
     ``boxes [B,R,6]`` normalized, ``image_shape = (H, W, D)`` of the input volume, ``feature_maps`` = four CUDA
     tensors ``[B,H_l,W_l,D_l,C]``.  Returns ``[B,R,ph,pw,pd,C]`` in the boxes' order; differentiable w.r.t. the
-    feature maps (boxes are stop_gradient'ed upstream, core/models.py:660)."""
+    feature maps (boxes are stop_gradient'ed upstream, core/models.py:660).  ``out_dtype=torch.float16`` writes the
+    target files' ``rois_aligned`` payload directly (core/models.py:3613; inference only, bit-identical to
+    ``pack_f16`` of the float32 result)."""
     dev = _device()
     for t in list(feature_maps) + [boxes]:
         if not (isinstance(t, torch.Tensor) and t.device.type == "cuda" and t.dtype == torch.float32):
             raise InvalidArgumentError("pyramid_roi_align_3d takes float32 CUDA tensors")
     _require(boxes.dim() == 3 and boxes.shape[2] == 6, "boxes must be [B, R, 6]")
     _require(all(fm.dim() == 5 and fm.shape[0] == boxes.shape[0] for fm in feature_maps), "feature maps must be [B,H,W,D,C]")
-    del dev
+    if out_dtype == torch.float16:
+        fms = [t.contiguous() for t in feature_maps]
+        boxes = boxes.contiguous()
+        B, R = boxes.shape[:2]
+        C = fms[0].shape[4]
+        ps = tuple(int(v) for v in pool_shape)
+        out = torch.empty((B, R) + ps + (C,), dtype=torch.float16, device=dev)
+        ptrs, shapes, ishape = _pyr_args(fms, image_shape)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd_f16(ptrs, shapes, B, C, _ptr(boxes), R, ishape, ps[0], ps[1], ps[2],
+                                                               _ptr(out), _stream_ptr()))
+        return out
+    _require(out_dtype == torch.float32, "out_dtype must be float32 or float16")
     return PyramidROIAlign3DFunction.apply(boxes, tuple(image_shape), tuple(int(v) for v in pool_shape), *feature_maps)
 
 

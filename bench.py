@@ -315,6 +315,29 @@ def run_ours(args):
     fused = {"ms_per_step": round(fused_ms, 4), "value": round(world * total_rois / (fused_ms * 1e-3), 1), "unit": UNIT,
              "launches_per_step": 4, "note": "roi3d_pyramid_roi_align_fwd/grad: routing + 4 levels + order restore in one "
              "launch per pool shape (7^3 uses the plane kernel here, the per-op path picks the direct kernel)"}
+    # float16 output (the target files' payload) written by the crop kernel vs float32 crop + separate conversion
+    f16 = {}
+    for c in CROPS:
+        def _f16(c=c):
+            return rb.pyramid_roi_align_3d(d_boxes_br, VOLUME, fms, c, out_dtype=torch.float16)
+
+        def _f32_then_pack(c=c):
+            with torch.no_grad():
+                return rb.pack_f16(rb.pyramid_roi_align_3d(d_boxes_br, VOLUME, fms, c))
+        ts = []
+        for fn in (_f16, _f32_then_pack):
+            ms = []
+            for it in range(12):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                if it >= 4:
+                    ms.append(a.elapsed_time(b))
+            ts.append(round(statistics.median(ms), 4))
+        f16["crop%d" % c[0]] = {"fused_f16_ms": ts[0], "f32_then_pack_ms": ts[1]}
+    fused["f16_output"] = f16
     del pooled, pgrads, gms
 
     # ---- NMS3D @6k boxes (cfg1: 6000 -> 1000 @0.7), device resident and host-buffer end to end ----

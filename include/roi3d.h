@@ -153,6 +153,11 @@ ROI3D_API int roi3d_car3d_grad_boxes(const float *grads, const float *image,
 ROI3D_API int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
                                           const float *boxes, int rois_per_image, const float image_shape[3],
                                           int ph, int pw, int pd, float *pooled, roi3d_stream_t stream);
+/* float16 output: the `rois_aligned` payload of the head-target files (core/models.py:3613 `ra.astype(np.float16)`)
+ * written by the crop kernel itself -- bit-identical to roi3d_pack_f16 of the float32 result, half the bytes. */
+ROI3D_API int roi3d_pyramid_roi_align_fwd_f16(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                              const float *boxes, int rois_per_image, const float image_shape[3],
+                                              int ph, int pw, int pd, void *pooled_f16, roi3d_stream_t stream);
 ROI3D_API int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], const int level_shapes[4][3],
                                            int B, int C, const float *boxes, int rois_per_image,
                                            const float image_shape[3], int ph, int pw, int pd, roi3d_stream_t stream);

@@ -428,6 +428,15 @@ def test_fused_pyramid_roi_align(rb, cuda_device, pool):
     ref = oracle.pyramid_roi_align(boxes, image_shape, fms, pool)
     assert out.shape == ref.shape
     assert np.array_equal(out.detach().cpu().numpy(), ref)
+    # float16 output mode = the target files' `rois_aligned` payload: bit-identical to astype(float16) of the above
+    fms[0][0, 5, 5, 7, 1] = 1e6                                 # overflows float16 -> inf, like numpy
+    with torch.no_grad():
+        h = rb.pyramid_roi_align_3d(dev(boxes, cuda_device), image_shape, [dev(f, cuda_device) for f in fms], pool,
+                                    out_dtype=torch.float16)
+    with np.errstate(over="ignore"):
+        href = oracle.pyramid_roi_align(boxes, image_shape, fms, pool).astype(np.float16)
+    assert h.dtype == torch.float16 and np.array_equal(h.cpu().numpy().view(np.uint16), href.view(np.uint16))
+    fms[0][0, 5, 5, 7, 1] = 0.5
     grads = rng.standard_normal(ref.shape, dtype=np.float32)
     out.backward(dev(grads, cuda_device))
     gref = oracle.pyramid_roi_align_grad(grads, boxes, image_shape, [f.shape for f in fms])
