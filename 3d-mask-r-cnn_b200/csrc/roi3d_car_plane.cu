@@ -75,31 +75,50 @@ __device__ __forceinline__ void build_axis_tables(PlaneShared &S, const CarGeom 
         T.cand[2 * k + 1] = c1;
     }
     __syncthreads();
-    {   // dedupe: candidate j is a "first" if no earlier candidate has its value
+    {   // dedupe: candidate j is a "first" if no earlier candidate has its value; list = firsts in order
         const int a = tid / (2 * PL_MAXP), j = tid % (2 * PL_MAXP);
         const int p = a ? g.pw : g.ph;
         AxisTab &T = S.ax[a];
-        int fo = j;
         const int v = T.cand[j];
-        if (j < 2 * p && v >= 0) {
-            for (int i = 0; i < j; ++i)
-                if (T.cand[i] == v) { fo = i; break; }
-        }
-        T.first[j] = (j < 2 * p && v >= 0 && fo == j) ? 1 : 0;
-        __syncthreads();
-        if (j < 2 * p) {
-            int pos = -1;
-            if (v >= 0) {
-                pos = 0;
-                for (int i = 0; i < fo; ++i) pos += T.first[i];
-                if (fo == j) T.list[pos] = v;
+        const bool fast = 2 * p <= 32;                        // the axis' candidates fit one warp (crops up to 16)
+        int fo = j;
+        if (fast) {
+            if (j < 32) {                                      // warp 0 (y) / warp 4 (x): match instead of searching
+                const bool valid = j < 2 * p && v >= 0;
+                const unsigned m = __match_any_sync(0xffffffffu, valid ? v : -1 - j);
+                fo = __ffs(m) - 1;
+                const bool isfirst = valid && fo == j;
+                const unsigned fb = __ballot_sync(0xffffffffu, isfirst);
+                if (j < 2 * p) {
+                    const int pos = valid ? __popc(fb & ((1u << fo) - 1u)) : -1;
+                    if (isfirst) T.list[pos] = v;
+                    if (j & 1) T.pos1[j >> 1] = (short)pos; else T.pos0[j >> 1] = (short)pos;
+                }
+                if (j == 0) T.n = __popc(fb);
             }
-            if (j & 1) T.pos1[j >> 1] = (short)pos; else T.pos0[j >> 1] = (short)pos;
+        } else {
+            if (j < 2 * p && v >= 0) {
+                for (int i = 0; i < j; ++i)
+                    if (T.cand[i] == v) { fo = i; break; }
+            }
+            T.first[j] = (j < 2 * p && v >= 0 && fo == j) ? 1 : 0;
         }
-        if (j == 2 * p - 1) {
-            int cnt = 0;
-            for (int i = 0; i < 2 * p; ++i) cnt += T.first[i];
-            T.n = cnt;
+        __syncthreads();
+        if (!fast) {
+            if (j < 2 * p) {
+                int pos = -1;
+                if (v >= 0) {
+                    pos = 0;
+                    for (int i = 0; i < fo; ++i) pos += T.first[i];
+                    if (fo == j) T.list[pos] = v;
+                }
+                if (j & 1) T.pos1[j >> 1] = (short)pos; else T.pos0[j >> 1] = (short)pos;
+            }
+            if (j == 2 * p - 1) {
+                int cnt = 0;
+                for (int i = 0; i < 2 * p; ++i) cnt += T.first[i];
+                T.n = cnt;
+            }
         }
     }
     __syncthreads();
@@ -113,6 +132,11 @@ __device__ __forceinline__ void build_y_tiles(PlaneShared &S, const CarGeom &g, 
         const int nx = max(S.ax[1].n, 1);
         int nt = 0, lo = 1 << 30, hi = -1, ya = 0;
         S.tile_y0[0] = 0;
+        if (Y.n * nx <= zcap && g.ph * g.pw <= PL_MAXOUT) {   // common case: the whole crop is one tile
+            S.tile_r0[0] = 0; S.tile_r1[0] = (short)(Y.n - 1);
+            S.tile_y0[1] = (short)g.ph;
+            S.ntiles = 1;
+        } else {
         for (int y = 0; y < g.ph; ++y) {
             const bool valid = Y.pos0[y] >= 0;
             const int a = min((int)Y.pos0[y], (int)Y.pos1[y]), b = max((int)Y.pos0[y], (int)Y.pos1[y]);
@@ -130,6 +154,7 @@ __device__ __forceinline__ void build_y_tiles(PlaneShared &S, const CarGeom &g, 
         S.tile_r0[nt] = (short)(hi < 0 ? 0 : lo); S.tile_r1[nt] = (short)hi;
         S.tile_y0[++nt] = (short)g.ph;
         S.ntiles = nt;
+        }
     }
     __syncthreads();
 }
