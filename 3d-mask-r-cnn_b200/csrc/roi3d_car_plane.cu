@@ -568,31 +568,26 @@ struct BwdLists {
 __device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, const CarGeom &g, unsigned ebytes)
 {
     const int tid = threadIdx.x;
-    if (tid < 2) {                                             // thread a: prefix of the counts of axis a
-        const AxisTab &T = S.ax[tid];
-        const int p = tid ? g.pw : g.ph;
-        int run = 0;
-        for (int q = 0; q < T.n; ++q) {
-            int c = 0;
-            for (int s = 0; s < p; ++s) c += (T.pos0[s] == q) + (T.pos1[s] == q);
-            B.start[tid][q] = (short)run;
-            B.cnt[tid][q] = (short)c;
-            run += c;
-        }
+    const int a = tid / (2 * PL_MAXP), q = tid % (2 * PL_MAXP);            // one thread per (axis, footprint position)
+    const bool mine = tid < 4 * PL_MAXP && q < S.ax[a].n;
+    const int p = a ? g.pw : g.ph;
+    if (mine) {
+        const AxisTab &T = S.ax[a];
+        int c = 0;
+        for (int s = 0; s < p; ++s) c += (T.pos0[s] == q) + (T.pos1[s] == q);
+        B.cnt[a][q] = (short)c;
     }
     __syncthreads();
-    if (tid < 4 * PL_MAXP) {                                    // one thread per (axis, position)
-        const int a = tid / (2 * PL_MAXP), q = tid % (2 * PL_MAXP);
+    if (mine) {
         const AxisTab &T = S.ax[a];
-        const int p = a ? g.pw : g.ph;
-        if (q < T.n) {
-            int w = B.start[a][q];
-            const unsigned unit = a ? ebytes : ebytes * (unsigned)g.pw;
-            for (int s = 0; s < p; ++s)
-                if (T.pos0[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, __fsub_rn(1.0f, T.t[s])}; ++w; }
-            for (int s = 0; s < p; ++s)
-                if (T.pos1[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, T.t[s]}; ++w; }
-        }
+        int w = 0;
+        for (int r = 0; r < q; ++r) w += B.cnt[a][r];                      // exclusive prefix (a dozen entries)
+        B.start[a][q] = (short)w;
+        const unsigned unit = a ? ebytes : ebytes * (unsigned)g.pw;
+        for (int s = 0; s < p; ++s)
+            if (T.pos0[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, __fsub_rn(1.0f, T.t[s])}; ++w; }
+        for (int s = 0; s < p; ++s)
+            if (T.pos1[s] == q) { B.samp[a][w] = (short)s; B.ent[a][w] = Contrib{(unsigned)s * unit, T.t[s]}; ++w; }
     }
     __syncthreads();
 }
