@@ -108,9 +108,10 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
     int variant = option_value(OPT_CAR_FWD_VARIANT);
     const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
                           ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(crops)) & 15) == 0;
-    // measured on B200 (profiles/variants_r1.txt): the plane-staged kernel wins once a depth slice has
-    // enough outputs to amortise its per-CTA tables (14^3: 2.1x), the direct gather wins at 7^3
-    if (variant == 0) variant = (plane_ok && C >= 32 && ph * pw >= 100) ? 2 : 1;
+    // measured on B200 (profiles/fwd_rule_sweep.py, variants_r1.txt): the plane-staged kernel wins once a depth slice
+    // has enough outputs to amortise its per-CTA tables -- from 10 x 10 at any channel count >= 32, from 7 x 7 when
+    // the channel chunks are full (C >= 128); below that the direct gather wins or ties
+    if (variant == 0) variant = (plane_ok && ((C >= 32 && ph * pw >= 100) || (C >= 128 && ph * pw >= 49))) ? 2 : 1;
     if (variant == 3 && plane_ok) {                                     // TMA-fed plane kernel (opt-in)
         const int rc = launch_car3d_fwd_plane_tma(image, boxes, box_index, g, extrapolation_value, crops, s);
         if (rc != ROI3D_EUNSUPPORTED) return rc;
