@@ -221,7 +221,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
                        void *__restrict__ crops, const PyrParams P)
 {
     using OutT = typename std::conditional<HALF, __half, float>::type;    // HALF: the target files' float16 payload
-    constexpr int UNR = (V == 1) ? 4 : 1;                      // stage-A voxels in flight per thread (x V x 2 taps);
+    constexpr int UNR = 1;                                     // stage-A voxels in flight per thread (x V x 2 taps);
                                                                // measured: less unrolling beats more here (72 regs, no spills)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
