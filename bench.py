@@ -482,15 +482,23 @@ def run_ours(args):
         2 * sum(x["boxes"].numel() * 4 + x["bidx"].numel() * 4 for x in h)
     d2h = sum(x["grads"].numel() * 4 for x in h) + sum(int(np.prod(op["shape"])) * 4 for op in ops)
 
+    # The 16 op nodes of a step are independent; like an executor that runs ready nodes first, the step issues the
+    # grad-image nodes of the EMPTY levels first (they need no upload: their zero-filled results start downloading
+    # while the maps are still going up), then the forward nodes, then the grad-image nodes that wait for their grads.
+    order_b0 = [i for i, op in enumerate(ops) if op["n"] == 0]
+    order_b1 = [i for i, op in enumerate(ops) if op["n"] > 0]
+
     def e2e_step():
         with rb.deferred():
+            outs = [None] * (2 * len(ops))
+            for i in order_b0:
+                outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
             d_img = {lv: t.to(dev, non_blocking=True) for lv, t in h_images.items()}
-            outs = []
-            for op, x in zip(ops, h):
+            for i, (op, x) in enumerate(zip(ops, h)):
                 # mixed call: device-resident map, host boxes -> host result
-                outs.append(rb.crop_and_resize_3d(d_img[op["level"]], x["boxes"], x["bidx"], op["crop"]))
-            for op, x in zip(ops, h):
-                outs.append(rb.crop_and_resize_3d_grad_image(x["grads"], x["boxes"], x["bidx"], op["shape"]))
+                outs[i] = rb.crop_and_resize_3d(d_img[op["level"]], x["boxes"], x["bidx"], op["crop"])
+            for i in order_b1:
+                outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
         return outs
 
     e2e_steps = max(2, min(args.steps, 5))
