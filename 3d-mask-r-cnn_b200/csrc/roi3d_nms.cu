@@ -104,16 +104,20 @@ nms_keys_kernel(const float *__restrict__ scores, NmsSeg seg, int kstride, unsig
     keys[(size_t)z * kstride + i] = (i < n) ? score_key(__ldg(scores + seg_begin(seg, z) + i)) : 0xFFFFFFFFu;
 }
 
+// DIRECT: single problem with 16-byte aligned scores -- the CTA converts the scores it stages itself (float4 loads), which
+// saves the key pre-pass launch; otherwise it stages the pre-computed keys.
+template <bool DIRECT>
 __global__ void __launch_bounds__(RS_THREADS)
-nms_rank_sort_kernel(const float *__restrict__ boxes, const unsigned *__restrict__ keys, int kstride, NmsSeg seg,
-                     int *__restrict__ sorted_idx, SBox *__restrict__ sboxes, int *__restrict__ nvalid_out,
-                     ScanState *__restrict__ state)
+nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, const unsigned *__restrict__ keys,
+                     int kstride, NmsSeg seg, int *__restrict__ sorted_idx, SBox *__restrict__ sboxes,
+                     int *__restrict__ nvalid_out, ScanState *__restrict__ state)
 {
     const int z = blockIdx.y, n = seg_size(seg, z);
     if (blockIdx.x > 0 && blockIdx.x * RS_ITILE >= n) return;          // CTA-uniform; CTA 0 still publishes nvalid
     {
         const int base = seg_begin(seg, z);
         boxes += (size_t)base * 6;
+        scores += base;
         keys += (size_t)z * kstride;
         sorted_idx += (size_t)z * seg.stride;
         sboxes += (size_t)z * seg.stride;
@@ -125,7 +129,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const unsigned *__restrict
     const int il = threadIdx.x / RS_JSPLIT;                   // box within the CTA's tile
     const int jq = threadIdx.x % RS_JSPLIT;                   // lane over the key tile
     const int i = blockIdx.x * RS_ITILE + il;
-    const unsigned ki = (i < n) ? __ldg(keys + i) : 0xFFFFFFFFu;
+    const unsigned ki = (i < n) ? (DIRECT ? score_key(__ldg(scores + i)) : __ldg(keys + i)) : 0xFFFFFFFFu;
     if (threadIdx.x < RS_ITILE) s_rank[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_valid = 0;
     int cnt = 0, nvalid = 0;
@@ -137,8 +141,22 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const unsigned *__restrict
         __syncthreads();
         const int tile = min(RS_KTILE, n - j0);
         const uint4 *src = reinterpret_cast<const uint4 *>(keys + j0);
+        const float4 *fsrc = reinterpret_cast<const float4 *>(scores + j0);
         for (int t = threadIdx.x; t < (tile + 3) / 4; t += RS_THREADS) {
-            const uint4 k4 = __ldg(src + t);
+            uint4 k4;
+            if constexpr (DIRECT) {
+                if (4 * t + 4 <= tile) {
+                    const float4 f = __ldg(fsrc + t);
+                    k4 = make_uint4(score_key(f.x), score_key(f.y), score_key(f.z), score_key(f.w));
+                } else {                                       // last, partial vector: pad with "not a candidate"
+                    const float *fs = scores + j0 + 4 * t;
+                    const int r = tile - 4 * t;
+                    k4 = make_uint4(score_key(__ldg(fs)), r > 1 ? score_key(__ldg(fs + 1)) : 0xFFFFFFFFu,
+                                    r > 2 ? score_key(__ldg(fs + 2)) : 0xFFFFFFFFu, 0xFFFFFFFFu);
+                }
+            } else {
+                k4 = __ldg(src + t);
+            }
             reinterpret_cast<uint4 *>(s_keys)[t] = k4;
             if (blockIdx.x == 0)
                 nvalid += (k4.x != 0xFFFFFFFFu) + (k4.y != 0xFFFFFFFFu) + (k4.z != 0xFFFFFFFFu) + (k4.w != 0xFFFFFFFFu);
@@ -670,9 +688,14 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
         nms_bucket_rank_kernel<<<dim3((n + 255) / 256, S), 256, 0, stream>>>(boxes, scores, seg, start, tkey, tidx, sidx, sboxes);
         ROI3D_LAUNCH_CHECK();
     } else {
-        nms_keys_kernel<<<dim3((L.kstride + 255) / 256, S), 256, 0, stream>>>(scores, seg, L.kstride, keys);
-        ROI3D_LAUNCH_CHECK();
-        nms_rank_sort_kernel<<<dim3((n + RS_ITILE - 1) / RS_ITILE, S), RS_THREADS, 0, stream>>>(boxes, keys, L.kstride, seg, sidx, sboxes, nvalid, state);
+        const dim3 rgrid((n + RS_ITILE - 1) / RS_ITILE, S);
+        if (segments <= 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0) {
+            nms_rank_sort_kernel<true><<<rgrid, RS_THREADS, 0, stream>>>(boxes, scores, keys, L.kstride, seg, sidx, sboxes, nvalid, state);
+        } else {
+            nms_keys_kernel<<<dim3((L.kstride + 255) / 256, S), 256, 0, stream>>>(scores, seg, L.kstride, keys);
+            ROI3D_LAUNCH_CHECK();
+            nms_rank_sort_kernel<false><<<rgrid, RS_THREADS, 0, stream>>>(boxes, scores, keys, L.kstride, seg, sidx, sboxes, nvalid, state);
+        }
         ROI3D_LAUNCH_CHECK();
     }
     const size_t smem = ((size_t)2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);

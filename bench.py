@@ -243,6 +243,7 @@ def run_ours(args):
         e1.record()
         barrier()
     launches = launches_per_step * args.steps if graph is not None else rb.kernel_launches()
+    ms_by_rank = [round(v / args.steps, 4) for v in rb.sharding.gather_over_ranks(e0.elapsed_time(e1))]
     ms_total = rb.sharding.max_over_ranks(e0.elapsed_time(e1))     # device time, slowest rank
     ms_step = ms_total / args.steps
     value = world * total_rois / (ms_step * 1e-3)
@@ -525,6 +526,7 @@ def run_ours(args):
                    "launch": (("CUDA graph replay of the %d C-ABI calls" % (2 * len(ops))) if graph is not None else "eager C-ABI calls") +
                              ("; independent op nodes of each phase on %d streams (forward phase joins before the backward phase)" % args.op_streams
                               if args.op_streams > 1 else "; one stream")},
+        "ms_per_step_by_rank": ms_by_rank,
         "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -657,3 +657,15 @@ def test_nms_bucketed_sort(rb, cuda_device, n, max_out, dist):
             assert np.array_equal(run_nms(rb, cuda_device, boxes, scores, max_out, 0.5), ref), variant
     finally:
         rb.custom_op.set_option("nms_sort_variant", 0)
+
+
+def test_nms_unaligned_scores_and_tail_vectors(rb, cuda_device):
+    """The rank sort stages scores with 16-byte loads when it can; views that are not 16-byte aligned and lengths that
+    are not multiples of four take the pre-computed-key path / the padded tail and return the same result."""
+    for n in (5, 6, 7, 1001, 1002, 1003, 6001):
+        boxes, scores = roi3d_synth.nms_boxes(n + 1, (128, 128, 128), seed=500 + n)
+        tb, ts = dev(boxes, cuda_device), dev(scores, cuda_device)
+        for off in (0, 1):
+            ref = oracle.non_max_suppression_3d(boxes[off:], scores[off:], 300, 0.5)
+            got = rb.non_max_suppression_3d(tb[off:], ts[off:], 300, 0.5).cpu().numpy()
+            assert np.array_equal(got, ref), (n, off)

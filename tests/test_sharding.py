@@ -41,6 +41,7 @@ def _worker(rank, world, port, q):
     nms_keep = {i: oracle.non_max_suppression_3d(boxes[bidx == i], rng.random(int((bidx == i).sum())).astype(np.float32) * 0 + 1, 5, 0.5)
                 for i in sh.images_of_rank(B, world, rank)}
     slowest = sh.max_over_ranks(10.0 + rank)
+    assert sh.gather_over_ranks(10.0 + rank) == [10.0 + r for r in range(world)]
     gathered = [None] * world
     dist.all_gather_object(gathered, (crops, pos, gimg, sh.images_of_rank(B, world, rank), nms_keep, slowest))
     if rank == 0:
