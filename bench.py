@@ -91,10 +91,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, enabled=True):
+        self.rows, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -144,8 +146,8 @@ def run_ours(args):
     vp = ctypes.c_void_p
     stream = lambda: vp(torch.cuda.current_stream().cuda_stream)   # noqa: E731
 
-    ops = make_workload(seed=2002 + rank)
-    seed_is_default = rank == 0            # the ncu traffic figures were captured on rank 0's ROI set
+    ops = make_workload(seed=2002)         # weak scaling: every rank runs the SAME batch, so per-GPU work is fixed exactly
+    seed_is_default = True                 # (the ncu traffic figures were captured on this ROI set)
     total_rois = BATCH * ROIS_PER_IMAGE
     # ---- device-resident state ---------------------------------------------------------------
     images = {}
@@ -223,7 +225,7 @@ def run_ours(args):
     run_step = graph.replay if graph is not None else step
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:      # one nvidia-smi poller per job, not per rank
         # the sampler runs from the warm-up (same kernels, same load) through the timed region so that a
         # millisecond-scale region still yields several nvidia-smi samples under load
         t_w = time.perf_counter()
