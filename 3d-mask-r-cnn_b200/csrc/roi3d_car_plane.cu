@@ -289,12 +289,14 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
             const int r = idx / nx, cx = idx - r * nx;
             voff[idx] = (unsigned)Y.list[r0 + r] * sH + (unsigned)X.list[cx] * sW;
         }
+        int my_bad = 0;
         for (int idx = threadIdx.x; idx < nout; idx += PL_THREADS) {
             const int yy = idx / g.pw, x = idx - yy * g.pw, y = ya + yy;
             const int py0 = Y.pos0[y], px0 = X.pos0[x];
             OutEntry e;
             if (py0 < 0 || px0 < 0) {
                 e.o_top = 0xFFFFFFFFu; e.o_bot = 0xFFFFFFFFu; e.xl = 0.f; e.yl = 0.f;
+                my_bad = 1;
             } else {
                 const unsigned rt = (unsigned)(py0 - r0) * nx, rb = (unsigned)(Y.pos1[y] - r0) * nx;
                 const unsigned px1 = (unsigned)X.pos1[x];
@@ -304,7 +306,9 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
             }
             otab[idx] = e;
         }
-        __syncthreads();
+        // the barrier doubles as the vote: tiles whose samples all lie inside the volume (the usual case) run
+        // stage B without the per-output extrapolation selects
+        const bool tile_has_bad = __syncthreads_or(my_bad) != 0;
 
         for (int k = k0; k < k1; ++k) {
             const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
@@ -364,27 +368,32 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
                 }
             }
             // ---- stage B: x-lerp, y-lerp from the plane -> crops ----------------------
+            auto stage_b = [&](auto has_bad_t) {
+                constexpr bool HAS_BAD = decltype(has_bad_t)::value;
 #pragma unroll 1
-            for (int idx = slot; idx < nout; idx += vs, o += ostride) {
-                const uint4 e = lds128u(otab_u32 + idx * 16);
-                const bool bad = e.x == 0xFFFFFFFFu;
-                const unsigned et = bad ? 0u : e.x, eb = bad ? 0u : e.y;
-                const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
-                const unsigned a_tl = z_u32 + (et & 0xFFFFu), a_tr = z_u32 + (et >> 16);
-                const unsigned a_bl = z_u32 + (eb & 0xFFFFu), a_br = z_u32 + (eb >> 16);
+                for (int idx = slot; idx < nout; idx += vs, o += ostride) {
+                    const uint4 e = lds128u(otab_u32 + idx * 16);
+                    const bool bad = HAS_BAD && e.x == 0xFFFFFFFFu;
+                    const unsigned et = bad ? 0u : e.x, eb = bad ? 0u : e.y;
+                    const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
+                    const unsigned a_tl = z_u32 + (et & 0xFFFFu), a_tr = z_u32 + (et >> 16);
+                    const unsigned a_bl = z_u32 + (eb & 0xFFFFu), a_br = z_u32 + (eb >> 16);
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    if (von[v]) {
-                        const unsigned vo = v * (cl * 16);
-                        const float4 tlv = lds128(a_tl + vo), trv = lds128(a_tr + vo);
-                        const float4 blv = lds128(a_bl + vo), brv = lds128(a_br + vo);
-                        const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
-                        float4 res = sel4(bad, ext4, lerp_rn(top, bot, yl));
-                        if constexpr (PYR) res = scrub4(res);
-                        st_stream4(o + v * vstep, res);
+                    for (int v = 0; v < V; ++v) {
+                        if (von[v]) {
+                            const unsigned vo = v * (cl * 16);
+                            const float4 tlv = lds128(a_tl + vo), trv = lds128(a_tr + vo);
+                            const float4 blv = lds128(a_bl + vo), brv = lds128(a_br + vo);
+                            const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
+                            float4 res = lerp_rn(top, bot, yl);
+                            if constexpr (HAS_BAD) res = sel4(bad, ext4, res);
+                            if constexpr (PYR) res = scrub4(res);
+                            st_stream4(o + v * vstep, res);
+                        }
                     }
                 }
-            }
+            };
+            if (tile_has_bad) stage_b(std::true_type{}); else stage_b(std::false_type{});
             __syncthreads();
         }
     }
