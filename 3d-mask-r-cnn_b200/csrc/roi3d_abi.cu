@@ -19,6 +19,7 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_lanes_v")) return OPT_CAR_V;
     if (!strcmp(name, "car_ctas_per_sm_target")) return OPT_KSPLIT;
     if (!strcmp(name, "nms_sort_variant")) return OPT_NMS_SORT;
+    if (!strcmp(name, "nms_pdl")) return OPT_NMS_PDL;
     return -1;
 }
 

@@ -17,7 +17,7 @@ namespace roi3d {
 extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
-enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_COUNT };
+enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_NMS_PDL = 6, OPT_COUNT };
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -111,6 +111,26 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, uns
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// be scheduled while its predecessor still runs; it must execute pdl_wait() before touching anything the predecessor
+// wrote (the wait returns when the predecessor grid has completed and flushed).  pdl_trigger() in the predecessor lets
+// the successor's launch latency overlap with the predecessor's execution.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                    Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- shared memory through 32-bit addresses (no generic->shared window math in the loops) ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) {

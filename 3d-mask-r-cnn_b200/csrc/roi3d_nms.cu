@@ -112,6 +112,7 @@ nms_rank_sort_kernel(const float *__restrict__ boxes, const float *__restrict__ 
                      int kstride, NmsSeg seg, int *__restrict__ sorted_idx, SBox *__restrict__ sboxes,
                      int *__restrict__ nvalid_out, ScanState *__restrict__ state)
 {
+    pdl_trigger();                                                     // the mask kernel may start launching
     const int z = blockIdx.y, n = seg_size(seg, z);
     if (blockIdx.x > 0 && blockIdx.x * RS_ITILE >= n) return;          // CTA-uniform; CTA 0 still publishes nvalid
     {
@@ -303,6 +304,7 @@ nms_bucket_rank_kernel(const float *__restrict__ boxes, const float *__restrict_
                        const int *__restrict__ start, const unsigned *__restrict__ tkey, const int *__restrict__ tidx,
                        int *__restrict__ sorted_idx, SBox *__restrict__ sboxes)
 {
+    pdl_trigger();
     const int z = blockIdx.y, n = seg_size(seg, z);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -351,6 +353,8 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
     // triangle (word_begin = 0, row_end = T), the tail phase everything right of it (word_begin = T / 32, all rows) --
     // unless the head phase's scan already finished (state->done), which is the common case when max_out << n.
     __shared__ float4 s_rows[ROWS * 2];
+    pdl_wait();                                                          // predecessor (sort / head scan) complete
+    pdl_trigger();
     const int z = blockIdx.z, n = min(seg_size(seg, z), row_end);
     if (state != nullptr && state[z].done) return;                       // CTA-uniform
     const int i0 = blockIdx.y * ROWS;
@@ -481,6 +485,8 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         keep_count += z;
         state += z;
     }
+    pdl_wait();                                                // predecessor (the phase's mask kernel) complete
+    pdl_trigger();
     const int4 st0 = *reinterpret_cast<const int4 *>(state);   // {nsel, done, nvalid, -}
     if (st0.y) return;                                         // CTA-uniform (written by the previous phase)
     const int nvalid = st0.z;
@@ -705,6 +711,7 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     // to whole super-chunks) get their own mask triangle and scan; the rest of the mask (the bulk of the n^2 / 2
     // pairs) and the tail scan are launched behind it and return immediately when the head already finished.
     // nms_variant 1 forces the single-phase schedule.
+    const bool pdl = option_value(OPT_NMS_PDL) == 0;
     const int nsb = (n + SC_SB - 1) / SC_SB;
     int head_sb = (int)(((long long)max_out + max_out / 4 + 256 + SC_SB - 1) / SC_SB);
     if (option_value(OPT_NMS_VARIANT) == 1 || head_sb >= nsb) head_sb = nsb;
@@ -713,22 +720,28 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
         const int words = (T + 31) / 32;
         const int hrows = (head_sb < nsb) ? 32 : MK_ROWS;      // a small head triangle needs more, smaller CTAs
         dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (T + hrows - 1) / hrows, S);
+        const ScanState *no_state = nullptr;
         if (hrows == 32)
-            nms_mask_kernel<32><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
+            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<32>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
+                                            L.pitch_words, thr, 0, T, no_state, mask));
         else
-            nms_mask_kernel<MK_ROWS><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, 0, T, nullptr, mask);
+            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
+                                            L.pitch_words, thr, 0, T, no_state, mask));
         ROI3D_LAUNCH_CHECK();
-        nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, 0, head_sb,
-                                                        state, krows, keep_idx, keep_count);
+        ROI3D_CUDA_TRY(launch_dependent(nms_scan_kernel, dim3(S), dim3(SC_THREADS), smem, stream, pdl, (const unsigned *)mask, L.pitch_words,
+                                        (const SBox *)sboxes, (const int *)sidx, (const int *)nvalid, n, max_out, thr, 0, head_sb, state,
+                                        krows, keep_idx, keep_count));
         ROI3D_LAUNCH_CHECK();
     }
     if (head_sb < nsb) {
         const int wb = T / 32, words = (n + 31) / 32 - wb;
         dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
-        nms_mask_kernel<MK_ROWS><<<mgrid, MK_WARPS * 32, 0, stream>>>(sboxes, seg, L.pitch_words, thr, wb, n, state, mask);
+        ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
+                                        L.pitch_words, thr, wb, n, (const ScanState *)state, mask));
         ROI3D_LAUNCH_CHECK();
-        nms_scan_kernel<<<S, SC_THREADS, smem, stream>>>(mask, L.pitch_words, sboxes, sidx, nvalid, n, max_out, thr, head_sb, nsb,
-                                                        state, krows, keep_idx, keep_count);
+        ROI3D_CUDA_TRY(launch_dependent(nms_scan_kernel, dim3(S), dim3(SC_THREADS), smem, stream, pdl, (const unsigned *)mask, L.pitch_words,
+                                        (const SBox *)sboxes, (const int *)sidx, (const int *)nvalid, n, max_out, thr, head_sb, nsb, state,
+                                        krows, keep_idx, keep_count));
         ROI3D_LAUNCH_CHECK();
     }
     return ROI3D_OK;

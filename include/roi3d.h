@@ -241,6 +241,8 @@ ROI3D_API int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y
  *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
  *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane kernels
  *   "nms_variant"       0 = speculative head/tail schedule, 1 = single phase (full mask, then one scan)
+ *   "nms_pdl"           0 = the mask / scan kernels are launched with programmatic dependent launch (their launch
+ *                       latency overlaps the predecessor), 1 = plain stream order
  *   "nms_sort_variant"  0 = auto (bucketed from 8192 boxes), 1 = rank by counting, 2 = bucketed sort
  *   "car_ctas_per_sm_target"   grid sizing of the plane kernels: depth-sample splits are chosen so that about this
  *                       many CTAs per SM exist (0 = default 16)
