@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256)
 decode_proposals_kernel(const float *__restrict__ anchors, const float *__restrict__ deltas, const int *__restrict__ index,
                         int n, Std6 std, float min_dz, float *__restrict__ boxes)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t src = index ? (size_t)__ldg(index + i) : (size_t)i;
@@ -98,7 +100,7 @@ int launch_decode_proposals(const float *anchors, const float *deltas, const int
     const float depth = image_depth > 1.0f ? image_depth : 1.0f;
     const float inv = 1.0f / depth;
     const float min_dz = inv > 1e-4f ? inv : 1e-4f;
-    decode_proposals_kernel<<<(n + 255) / 256, 256, 0, stream>>>(anchors, deltas, index, n, s, min_dz, boxes);
+    ROI3D_CUDA_TRY(launch_dependent(decode_proposals_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, true, anchors, deltas, index, n, s, min_dz, boxes));
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
@@ -137,6 +139,8 @@ __device__ __forceinline__ int tk_bits(int p) { return p == 2 ? 10 : 11; }
 __global__ void __launch_bounds__(TK_THREADS)
 topk_hist_kernel(const float *__restrict__ scores, int n, int pass, TopkState *__restrict__ st)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     __shared__ unsigned s_hist[2048];
     for (int t = threadIdx.x; t < 2048; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
@@ -157,6 +161,8 @@ topk_hist_kernel(const float *__restrict__ scores, int n, int pass, TopkState *_
 __global__ void __launch_bounds__(TK_THREADS)
 topk_pick_kernel(int pass, int k_total, TopkState *__restrict__ st)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     __shared__ unsigned s_cnt[2048];
     __shared__ unsigned s_sum[TK_THREADS];
     const int nb = tk_bits(pass), bins = 1 << nb, shift = tk_shift(pass);
@@ -191,6 +197,8 @@ __global__ void __launch_bounds__(TK_THREADS)
 topk_count_kernel(const float *__restrict__ scores, int n, int range, const TopkState *__restrict__ st,
                   unsigned *__restrict__ less_cnt, unsigned *__restrict__ eq_cnt)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     __shared__ unsigned s_less, s_eq;
     if (threadIdx.x == 0) { s_less = 0; s_eq = 0; }
     __syncthreads();
@@ -213,6 +221,8 @@ __global__ void __launch_bounds__(TK_THREADS)
 topk_scan_kernel(int nblocks, const TopkState *__restrict__ st, const unsigned *__restrict__ less_cnt,
                  const unsigned *__restrict__ eq_cnt, unsigned *__restrict__ eq_off, unsigned *__restrict__ sel_off)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     __shared__ unsigned s_a[TK_THREADS];
     const unsigned need_eq = st->need;
     const int t = threadIdx.x;
@@ -245,6 +255,8 @@ topk_compact_kernel(const float *__restrict__ scores, int n, int range, const To
                     const unsigned *__restrict__ eq_off, const unsigned *__restrict__ sel_off,
                     int *__restrict__ idx_out, float *__restrict__ scores_out)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     __shared__ unsigned s_warp[2][32];
     __shared__ unsigned s_base[2];
     const unsigned T = st->prefix, need_eq = st->need;
@@ -292,6 +304,8 @@ __global__ void __launch_bounds__(256)
 gather_pad_boxes_kernel(const float *__restrict__ boxes, const int *__restrict__ keep, const int *__restrict__ count,
                         int p, float *__restrict__ out)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p * 6) return;
     const int r = t / 6, c = t - r * 6;
@@ -325,23 +339,23 @@ int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_o
     ROI3D_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(TopkState), stream));
     const int hgrid = min((n + TK_THREADS - 1) / TK_THREADS, kNumSMs * 2);
     for (int pass = 0; pass < 3; ++pass) {
-        topk_hist_kernel<<<hgrid, TK_THREADS, 0, stream>>>(scores, n, pass, st);
+        ROI3D_CUDA_TRY(launch_dependent(topk_hist_kernel, dim3(hgrid), dim3(TK_THREADS), 0, stream, true, scores, n, pass, st));
         ROI3D_LAUNCH_CHECK();
-        topk_pick_kernel<<<1, TK_THREADS, 0, stream>>>(pass, k, st);
+        ROI3D_CUDA_TRY(launch_dependent(topk_pick_kernel, dim3(1), dim3(TK_THREADS), 0, stream, true, pass, k, st));
         ROI3D_LAUNCH_CHECK();
     }
-    topk_count_kernel<<<nblocks, TK_THREADS, 0, stream>>>(scores, n, range, st, less_cnt, eq_cnt);
+    ROI3D_CUDA_TRY(launch_dependent(topk_count_kernel, dim3(nblocks), dim3(TK_THREADS), 0, stream, true, scores, n, range, (const TopkState *)st, less_cnt, eq_cnt));
     ROI3D_LAUNCH_CHECK();
-    topk_scan_kernel<<<1, TK_THREADS, 0, stream>>>(nblocks, st, less_cnt, eq_cnt, eq_off, sel_off);
+    ROI3D_CUDA_TRY(launch_dependent(topk_scan_kernel, dim3(1), dim3(TK_THREADS), 0, stream, true, nblocks, (const TopkState *)st, (const unsigned *)less_cnt, (const unsigned *)eq_cnt, eq_off, sel_off));
     ROI3D_LAUNCH_CHECK();
-    topk_compact_kernel<<<nblocks, TK_THREADS, 0, stream>>>(scores, n, range, st, eq_off, sel_off, idx_out, scores_out);
+    ROI3D_CUDA_TRY(launch_dependent(topk_compact_kernel, dim3(nblocks), dim3(TK_THREADS), 0, stream, true, scores, n, range, (const TopkState *)st, (const unsigned *)eq_off, (const unsigned *)sel_off, idx_out, scores_out));
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
 
 int launch_gather_pad_boxes(const float *boxes, const int *keep, const int *count, int p, float *out, cudaStream_t stream)
 {
-    gather_pad_boxes_kernel<<<(p * 6 + 255) / 256, 256, 0, stream>>>(boxes, keep, count, p, out);
+    ROI3D_CUDA_TRY(launch_dependent(gather_pad_boxes_kernel, dim3((p * 6 + 255) / 256), dim3(256), 0, stream, true, boxes, keep, count, p, out));
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }

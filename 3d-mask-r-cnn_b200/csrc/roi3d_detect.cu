@@ -36,6 +36,8 @@ refine_decode_kernel(const float *__restrict__ rois, const float *__restrict__ p
                      int total, int rois_per_image, int images, int num_classes, RefineParams P,
                      float *__restrict__ boxes_px, float *__restrict__ scores, int *__restrict__ seg_offsets)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= images) seg_offsets[i] = i * rois_per_image;
     if (i >= total) return;
@@ -73,6 +75,8 @@ refine_gather_kernel(const float *__restrict__ boxes_px, const float *__restrict
                      const int *__restrict__ count, int rois_per_image, int max_inst, int images, RefineParams P,
                      float *__restrict__ det, int *__restrict__ det_count)
 {
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (det_count && t < images) det_count[t] = min(count[t], max_inst);
     if (t >= images * max_inst * 8) return;
@@ -126,15 +130,16 @@ int launch_refine_detections(const float *rois, const float *probs, const float 
     const int total = images * rois_per_image;
     ROI3D_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)images, stream));
     if (total > 0) {
-        refine_decode_kernel<<<(max(total, images + 1) + 255) / 256, 256, 0, stream>>>(rois, probs, deltas, total, rois_per_image,
-                                                                                    images, num_classes, P, boxes_px, scores, offs);
+        ROI3D_CUDA_TRY(launch_dependent(refine_decode_kernel, dim3((max(total, images + 1) + 255) / 256), dim3(256), 0, stream, true, rois, probs,
+                                        deltas, total, rois_per_image, images, num_classes, P, boxes_px, scores, offs));
         ROI3D_LAUNCH_CHECK();
         const int rc = launch_nms3d(boxes_px, scores, offs, images, rois_per_image, max_inst, nms_thr, keep, count,
                                     base + L.nms, ws_bytes - L.nms, stream);
         if (rc != ROI3D_OK) return rc;
     }
-    refine_gather_kernel<<<(images * max_inst * 8 + 255) / 256, 256, 0, stream>>>(boxes_px, scores, keep, count, rois_per_image,
-                                                                                 max_inst, images, P, detections, det_count);
+    ROI3D_CUDA_TRY(launch_dependent(refine_gather_kernel, dim3((images * max_inst * 8 + 255) / 256), dim3(256), 0, stream, true,
+                                    (const float *)boxes_px, (const float *)scores, (const int *)keep, (const int *)count, rois_per_image,
+                                    max_inst, images, P, detections, det_count));
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
