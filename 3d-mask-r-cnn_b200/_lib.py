@@ -34,6 +34,7 @@ EXPORTS = [
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
     "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_fwd_f16", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
     "roi3d_topk_workspace_bytes", "roi3d_topk", "roi3d_gather_pad_boxes",
+    "roi3d_proposal_layer_workspace_bytes", "roi3d_proposal_layer",
     "roi3d_refine_detections_workspace_bytes", "roi3d_refine_detections", "roi3d_mask_targets",
     "roi3d_pack_f16", "roi3d_unpack_f16", "roi3d_pack_bits", "roi3d_unpack_bits",
     "roi3d_set_option", "roi3d_get_option", "roi3d_kernel_launches", "roi3d_reset_kernel_launches",
@@ -111,6 +112,10 @@ def _declare(lib):
     lib.roi3d_topk_workspace_bytes.argtypes = [i]
     lib.roi3d_topk.restype = i
     lib.roi3d_topk.argtypes = [vp, i, i, vp, vp, vp, sz, vp]
+    lib.roi3d_proposal_layer_workspace_bytes.restype = sz
+    lib.roi3d_proposal_layer_workspace_bytes.argtypes = [i, i, i]
+    lib.roi3d_proposal_layer.restype = i
+    lib.roi3d_proposal_layer.argtypes = [vp, vp, vp, i, vp, f, i, i, f, vp, vp, vp, sz, vp]
     lib.roi3d_gather_pad_boxes.restype = i
     lib.roi3d_gather_pad_boxes.argtypes = [vp, vp, vp, i, vp, vp]
     ll = ctypes.c_longlong

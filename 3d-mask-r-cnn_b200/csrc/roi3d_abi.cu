@@ -262,6 +262,61 @@ int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y, roi3d_st
     return launch_unpack_bits(bits, n, y, static_cast<cudaStream_t>(stream));
 }
 
+// ---- ProposalLayer for one image in a single call (top-k -> decode -> NMS3D -> gather/pad), no host sync ----
+struct ProposalLayout { size_t idx, val, boxes, keep, topk, nms, total; };
+static ProposalLayout proposal_layout(int n, int k, int proposal_count) {
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    ProposalLayout L;
+    size_t off = 0;
+    L.idx = off;   off += up(sizeof(int) * (size_t)k);
+    L.val = off;   off += up(sizeof(float) * (size_t)k);
+    L.boxes = off; off += up(sizeof(float) * 6 * (size_t)k);
+    L.keep = off;  off += up(sizeof(int) * (size_t)(proposal_count > 0 ? proposal_count : 1));
+    L.topk = off;  off += up(topk_workspace_bytes(n));
+    L.nms = off;   off += up(nms3d_workspace_bytes(k, 0));
+    L.total = off;
+    return L;
+}
+
+size_t roi3d_proposal_layer_workspace_bytes(int n_anchors, int pre_nms_limit, int proposal_count)
+{
+    if (n_anchors <= 0 || pre_nms_limit <= 0) return 256;
+    return proposal_layout(n_anchors, pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors, proposal_count).total;
+}
+
+int roi3d_proposal_layer(const float *scores, const float *deltas, const float *anchors, int n_anchors,
+                         const float std_dev[6], float image_depth, int pre_nms_limit, int proposal_count,
+                         float nms_threshold, float *proposals, int *count, void *workspace, size_t workspace_bytes,
+                         roi3d_stream_t stream)
+{
+    if (n_anchors < 0 || pre_nms_limit < 0 || proposal_count < 0 || !std_dev || !count) return ROI3D_EINVAL;
+    if (!(nms_threshold >= 0.0f && nms_threshold <= 1.0f)) return ROI3D_EINVAL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int k = pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors;
+    if (proposal_count == 0) { ROI3D_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), s)); return ROI3D_OK; }
+    if (!proposals) return ROI3D_EINVAL;
+    if (k == 0) {
+        ROI3D_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), s));
+        ROI3D_CUDA_TRY(cudaMemsetAsync(proposals, 0, sizeof(float) * 6 * (size_t)proposal_count, s));
+        return ROI3D_OK;
+    }
+    if (!scores || !deltas || !anchors) return ROI3D_EINVAL;
+    const ProposalLayout L = proposal_layout(n_anchors, k, proposal_count);
+    if (!workspace || workspace_bytes < L.total || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ROI3D_EWORKSPACE;
+    char *base = static_cast<char *>(workspace);
+    int *idx = reinterpret_cast<int *>(base + L.idx);
+    float *val = reinterpret_cast<float *>(base + L.val);
+    float *boxes = reinterpret_cast<float *>(base + L.boxes);
+    int *keep = reinterpret_cast<int *>(base + L.keep);
+    int rc = launch_topk(scores, n_anchors, k, idx, val, base + L.topk, L.nms - L.topk, s);
+    if (rc != ROI3D_OK) return rc;
+    rc = launch_decode_proposals(anchors, deltas, idx, k, std_dev, image_depth, boxes, s);
+    if (rc != ROI3D_OK) return rc;
+    rc = launch_nms3d(boxes, val, nullptr, 0, k, proposal_count, nms_threshold, keep, count, base + L.nms, L.total - L.nms, s);
+    if (rc != ROI3D_OK) return rc;
+    return launch_gather_pad_boxes(boxes, keep, count, proposal_count, proposals, s);
+}
+
 static int pyramid_check(const int level_shapes[4][3], int B, int C, const float *boxes, int rois_per_image,
                          const float image_shape[3], int ph, int pw, int pd)
 {

@@ -566,24 +566,19 @@ def proposal_layer(scores, deltas, anchors, std_dev, image_depth, pre_nms_limit,
     dev = _device()
     sc, dl, an = _Arg(scores, torch.float32, dev), _Arg(deltas, torch.float32, dev), _Arg(anchors, torch.float32, dev)
     n = int(sc.dev.shape[0])
-    k = min(int(pre_nms_limit), n)
     P = int(proposal_count)
     lib = _lib.load()
     out = torch.empty((P, 6), dtype=torch.float32, device=dev)
-    count = torch.zeros(1, dtype=torch.int32, device=dev)
-    if k == 0 or P == 0:
-        return out.zero_(), count
-    idx, val = top_k_set(sc.dev, k)
-    boxes = torch.empty((k, 6), dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = lib.roi3d_proposal_layer_workspace_bytes(n, int(pre_nms_limit), P)
+    key = ("proposal", dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _ws_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     std = (ctypes.c_float * 6)(*[float(v) for v in std_dev])
-    _lib.check(lib.roi3d_decode_proposals(_ptr(an.dev), _ptr(dl.dev), _ptr(idx), k, std, float(image_depth), _ptr(boxes),
-                                          _stream_ptr()))
-    keep = torch.empty(P, dtype=torch.int32, device=dev)
-    nbytes = lib.roi3d_nms3d_workspace_bytes(k)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)        # separate from top_k_set's cached workspace
-    _lib.check(lib.roi3d_nms3d(_ptr(boxes), _ptr(val), k, P, float(nms_threshold), _ptr(keep), _ptr(count), _ptr(ws),
-                               ws.numel(), _stream_ptr()))
-    _lib.check(lib.roi3d_gather_pad_boxes(_ptr(boxes), _ptr(keep), _ptr(count), P, _ptr(out), _stream_ptr()))
+    _lib.check(lib.roi3d_proposal_layer(_ptr(sc.dev), _ptr(dl.dev), _ptr(an.dev), n, std, float(image_depth),
+                                        int(pre_nms_limit), P, float(nms_threshold), _ptr(out), _ptr(count), _ptr(ws),
+                                        ws.numel(), _stream_ptr()))
     return out, count
 
 

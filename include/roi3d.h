@@ -183,6 +183,14 @@ ROI3D_API int roi3d_topk(const float *scores, int n, int k, int *idx_out, float 
                          void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
 ROI3D_API int roi3d_gather_pad_boxes(const float *boxes, const int *keep_idx, const int *keep_count, int proposal_count,
                                      float *proposals, roi3d_stream_t stream);
+/* roi3d_proposal_layer    one image of ProposalLayer.call (core/models.py:382-500) in a single call: the four entry points
+ *                         above chained on `stream` (top-k of the foreground scores, decode, NMS3D, gather + zero-pad),
+ *                         no host synchronisation; count (device int32) receives the number of real proposals. */
+ROI3D_API size_t roi3d_proposal_layer_workspace_bytes(int n_anchors, int pre_nms_limit, int proposal_count);
+ROI3D_API int roi3d_proposal_layer(const float *scores, const float *deltas, const float *anchors, int n_anchors,
+                                   const float std_dev[6], float image_depth, int pre_nms_limit, int proposal_count,
+                                   float nms_threshold, float *proposals, int *count,
+                                   void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
 ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, const int *index, int n,
                                      const float std_dev[6], float image_depth, float *boxes, roi3d_stream_t stream);
 
