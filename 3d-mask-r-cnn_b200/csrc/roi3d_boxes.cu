@@ -127,6 +127,7 @@ __device__ __forceinline__ unsigned topk_key(float s) {
 struct TopkState {                  // lives in the workspace
     unsigned prefix;                // key bits decided so far (high bits)
     unsigned need;                  // how many elements still to take among the current prefix class
+    unsigned done_ctr;              // CTAs of the current kernel that have published their part (last one finishes the job)
     unsigned hist[2048];
 };
 
@@ -136,37 +137,12 @@ constexpr int TK_THREADS = 1024;
 __device__ __forceinline__ int tk_shift(int p) { return p == 0 ? 21 : (p == 1 ? 10 : 0); }
 __device__ __forceinline__ int tk_bits(int p) { return p == 2 ? 10 : 11; }
 
-__global__ void __launch_bounds__(TK_THREADS)
-topk_hist_kernel(const float *__restrict__ scores, int n, int pass, TopkState *__restrict__ st)
+// the CTA that publishes last finishes the pass: find the digit where the running count (best keys first) reaches
+// `need`, record it in the prefix and clear the histogram for the next pass
+__device__ __forceinline__ void tk_pick(int pass, int k_total, TopkState *__restrict__ st, unsigned *s_cnt, unsigned *s_sum)
 {
-    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
-    pdl_trigger();
-    __shared__ unsigned s_hist[2048];
-    for (int t = threadIdx.x; t < 2048; t += blockDim.x) s_hist[t] = 0;
-    __syncthreads();
-    const int shift = tk_shift(pass), nb = tk_bits(pass);
-    const unsigned prefix = st->prefix;
-    const int pshift = shift + nb;                               // bits above the current digit
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned k = topk_key(__ldg(scores + i));
-        if (pass == 0 || (k >> pshift) == (prefix >> pshift))
-            atomicAdd(&s_hist[(k >> shift) & ((1u << nb) - 1u)], 1u);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < 2048; t += blockDim.x)
-        if (s_hist[t]) atomicAdd(&st->hist[t], s_hist[t]);
-}
-
-// one CTA: find the digit where the running count (best keys first) reaches `need`; clear the histogram
-__global__ void __launch_bounds__(TK_THREADS)
-topk_pick_kernel(int pass, int k_total, TopkState *__restrict__ st)
-{
-    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
-    pdl_trigger();
-    __shared__ unsigned s_cnt[2048];
-    __shared__ unsigned s_sum[TK_THREADS];
     const int nb = tk_bits(pass), bins = 1 << nb, shift = tk_shift(pass);
-    for (int t = threadIdx.x; t < 2048; t += blockDim.x) { s_cnt[t] = st->hist[t]; st->hist[t] = 0; }
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) { s_cnt[t] = __ldcg(&st->hist[t]); st->hist[t] = 0; }
     __syncthreads();
     // inclusive scan of 2 bins per thread
     const unsigned a = (2 * threadIdx.x < bins) ? s_cnt[2 * threadIdx.x] : 0u;
@@ -180,26 +156,63 @@ topk_pick_kernel(int pass, int k_total, TopkState *__restrict__ st)
         __syncthreads();
     }
     const unsigned need = (pass == 0) ? (unsigned)k_total : st->need;
+    const unsigned prefix = (pass == 0) ? 0u : st->prefix;
     const unsigned before = s_sum[threadIdx.x] - (a + b);        // count of strictly better digits
     __syncthreads();
     // the digit d with before(d) < need <= before(d) + cnt(d)
     if (a && before < need && need <= before + a) {
-        st->prefix = (pass == 0 ? 0u : st->prefix) | ((unsigned)(2 * threadIdx.x) << shift);
+        st->prefix = prefix | ((unsigned)(2 * threadIdx.x) << shift);
         st->need = need - before;
     } else if (b && before + a < need && need <= before + a + b) {
-        st->prefix = (pass == 0 ? 0u : st->prefix) | ((unsigned)(2 * threadIdx.x + 1) << shift);
+        st->prefix = prefix | ((unsigned)(2 * threadIdx.x + 1) << shift);
         st->need = need - (before + a);
     }
+    if (threadIdx.x == 0) st->done_ctr = 0;
+}
+
+__device__ __forceinline__ bool tk_last_cta(TopkState *__restrict__ st)
+{
+    __shared__ bool s_last;
+    __threadfence();                                             // this CTA's results are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->done_ctr, 1u) == gridDim.x - 1;   // ... before it takes its ticket
+    __syncthreads();
+    return s_last;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_hist_kernel(const float *__restrict__ scores, int n, int pass, int k_total, TopkState *__restrict__ st)
+{
+    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
+    pdl_trigger();
+    __shared__ unsigned s_hist[2048];
+    __shared__ unsigned s_sum[TK_THREADS];
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    const int shift = tk_shift(pass), nb = tk_bits(pass);
+    const unsigned prefix = st->prefix;
+    const int pshift = shift + nb;                               // bits above the current digit
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned k = topk_key(__ldg(scores + i));
+        if (pass == 0 || (k >> pshift) == (prefix >> pshift))
+            atomicAdd(&s_hist[(k >> shift) & ((1u << nb) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x)
+        if (s_hist[t]) atomicAdd(&st->hist[t], s_hist[t]);
+    if (tk_last_cta(st)) tk_pick(pass, k_total, st, s_hist, s_sum);
 }
 
 // per-range counts of keys strictly better than / equal to the threshold key
 __global__ void __launch_bounds__(TK_THREADS)
-topk_count_kernel(const float *__restrict__ scores, int n, int range, const TopkState *__restrict__ st,
-                  unsigned *__restrict__ less_cnt, unsigned *__restrict__ eq_cnt)
+topk_count_kernel(const float *__restrict__ scores, int n, int range, int nblocks, TopkState *__restrict__ st,
+                  unsigned *__restrict__ less_cnt, unsigned *__restrict__ eq_cnt, unsigned *__restrict__ eq_off,
+                  unsigned *__restrict__ sel_off)
 {
     pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
     pdl_trigger();
     __shared__ unsigned s_less, s_eq;
+    __shared__ unsigned s_a[TK_THREADS];
     if (threadIdx.x == 0) { s_less = 0; s_eq = 0; }
     __syncthreads();
     const unsigned T = st->prefix;
@@ -214,39 +227,34 @@ topk_count_kernel(const float *__restrict__ scores, int n, int range, const Topk
     if ((threadIdx.x & 31) == 0) { if (l) atomicAdd(&s_less, l); if (e) atomicAdd(&s_eq, e); }
     __syncthreads();
     if (threadIdx.x == 0) { less_cnt[blockIdx.x] = s_less; eq_cnt[blockIdx.x] = s_eq; }
-}
-
-// one CTA: exclusive scans over the ranges -> eq_off[b] (rank of the range's first equal key) and sel_off[b]
-__global__ void __launch_bounds__(TK_THREADS)
-topk_scan_kernel(int nblocks, const TopkState *__restrict__ st, const unsigned *__restrict__ less_cnt,
-                 const unsigned *__restrict__ eq_cnt, unsigned *__restrict__ eq_off, unsigned *__restrict__ sel_off)
-{
-    pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
-    pdl_trigger();
-    __shared__ unsigned s_a[TK_THREADS];
-    const unsigned need_eq = st->need;
-    const int t = threadIdx.x;
-    const unsigned e = t < nblocks ? eq_cnt[t] : 0u, l = t < nblocks ? less_cnt[t] : 0u;
-    s_a[t] = e;
-    __syncthreads();
-    for (int o = 1; o < TK_THREADS; o <<= 1) {
-        const unsigned v = (t >= o) ? s_a[t - o] : 0u;
+    if (!tk_last_cta(st)) return;
+    // last CTA: exclusive scans over the ranges -> eq_off[b] (rank of the range's first equal key) and sel_off[b]
+    {
+        const unsigned need_eq = st->need;
+        const int t = threadIdx.x;
+        const unsigned ee = t < nblocks ? __ldcg(eq_cnt + t) : 0u, ll = t < nblocks ? __ldcg(less_cnt + t) : 0u;
+        s_a[t] = ee;
         __syncthreads();
-        s_a[t] += v;
+        for (int o = 1; o < TK_THREADS; o <<= 1) {
+            const unsigned v = (t >= o) ? s_a[t - o] : 0u;
+            __syncthreads();
+            s_a[t] += v;
+            __syncthreads();
+        }
+        const unsigned eoff = s_a[t] - ee;
+        const unsigned take = eoff >= need_eq ? 0u : min(ee, need_eq - eoff);
         __syncthreads();
+        s_a[t] = ll + take;
+        __syncthreads();
+        for (int o = 1; o < TK_THREADS; o <<= 1) {
+            const unsigned v = (t >= o) ? s_a[t - o] : 0u;
+            __syncthreads();
+            s_a[t] += v;
+            __syncthreads();
+        }
+        if (t < nblocks) { eq_off[t] = eoff; sel_off[t] = s_a[t] - (ll + take); }
+        if (t == 0) st->done_ctr = 0;
     }
-    const unsigned eoff = s_a[t] - e;
-    const unsigned take = eoff >= need_eq ? 0u : min(e, need_eq - eoff);
-    __syncthreads();
-    s_a[t] = l + take;
-    __syncthreads();
-    for (int o = 1; o < TK_THREADS; o <<= 1) {
-        const unsigned v = (t >= o) ? s_a[t - o] : 0u;
-        __syncthreads();
-        s_a[t] += v;
-        __syncthreads();
-    }
-    if (t < nblocks) { eq_off[t] = eoff; sel_off[t] = s_a[t] - (l + take); }
 }
 
 // index-ordered compaction of the selected set
@@ -339,14 +347,11 @@ int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_o
     ROI3D_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(TopkState), stream));
     const int hgrid = min((n + TK_THREADS - 1) / TK_THREADS, kNumSMs * 2);
     for (int pass = 0; pass < 3; ++pass) {
-        ROI3D_CUDA_TRY(launch_dependent(topk_hist_kernel, dim3(hgrid), dim3(TK_THREADS), 0, stream, true, scores, n, pass, st));
-        ROI3D_LAUNCH_CHECK();
-        ROI3D_CUDA_TRY(launch_dependent(topk_pick_kernel, dim3(1), dim3(TK_THREADS), 0, stream, true, pass, k, st));
+        ROI3D_CUDA_TRY(launch_dependent(topk_hist_kernel, dim3(hgrid), dim3(TK_THREADS), 0, stream, true, scores, n, pass, k, st));
         ROI3D_LAUNCH_CHECK();
     }
-    ROI3D_CUDA_TRY(launch_dependent(topk_count_kernel, dim3(nblocks), dim3(TK_THREADS), 0, stream, true, scores, n, range, (const TopkState *)st, less_cnt, eq_cnt));
-    ROI3D_LAUNCH_CHECK();
-    ROI3D_CUDA_TRY(launch_dependent(topk_scan_kernel, dim3(1), dim3(TK_THREADS), 0, stream, true, nblocks, (const TopkState *)st, (const unsigned *)less_cnt, (const unsigned *)eq_cnt, eq_off, sel_off));
+    ROI3D_CUDA_TRY(launch_dependent(topk_count_kernel, dim3(nblocks), dim3(TK_THREADS), 0, stream, true, scores, n, range, nblocks, st,
+                                    less_cnt, eq_cnt, eq_off, sel_off));
     ROI3D_LAUNCH_CHECK();
     ROI3D_CUDA_TRY(launch_dependent(topk_compact_kernel, dim3(nblocks), dim3(TK_THREADS), 0, stream, true, scores, n, range, (const TopkState *)st, (const unsigned *)eq_off, (const unsigned *)sel_off, idx_out, scores_out));
     ROI3D_LAUNCH_CHECK();

@@ -175,7 +175,7 @@ ROI3D_API int roi3d_overlaps3d(const float *boxes1, int n, const float *boxes2, 
 /* roi3d_topk              replaces tf.nn.top_k(scores, k) ahead of NMS (core/models.py:403-404): the selected SET equals
  *                         TF's (threshold ties -> lower indices); idx_out [k] is in ASCENDING INDEX order (the NMS that
  *                         follows orders by (score, position) itself, so ties resolve as with top_k's sorted output);
- *                         scores_out [k] optional.  3-pass radix select + ordered compaction, 9 launches, no host sync.
+ *                         scores_out [k] optional.  3-pass radix select + ordered compaction, 5 launches (the CTA that finishes last closes each pass), no host sync.
  * roi3d_gather_pad_boxes  replaces tf.gather(boxes, idx) + tf.pad to proposal_count (core/models.py:476-484); the keep
  *                         count is read on the device, so ProposalLayer needs no host synchronisation at all. */
 ROI3D_API size_t roi3d_topk_workspace_bytes(int n);
