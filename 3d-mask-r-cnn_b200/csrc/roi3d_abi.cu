@@ -133,14 +133,18 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     if (!geom_supported(g)) return ROI3D_EUNSUPPORTED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the op's contract: the whole output is defined (GI.so@0x3ec5 zero-fills it)
-    ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
-    if (n == 0) return ROI3D_OK;
-    if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;
     int variant = option_value(OPT_CAR_BWD_VARIANT);
     const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
                           ((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(grad_image)) & 15) == 0;
     if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
-    if (variant == 2 && plane_ok) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s);
+    const bool plane = n > 0 && variant == 2 && plane_ok && grads && boxes && box_ind;
+    // plane path: the zero-fill is a kernel that the scatter kernel overlaps with (programmatic dependent launch;
+    // option "nms_pdl" = 1 restores memset + plain stream order)
+    const bool fused_fill = plane && option_value(OPT_NMS_PDL) == 0;
+    if (!fused_fill) ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
+    if (n == 0) return ROI3D_OK;
+    if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;
+    if (plane) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill);
     return launch_car3d_grad_image_direct(grads, boxes, box_ind, g, method, grad_image, s);
 }
 

@@ -718,6 +718,9 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
                         if (von[v]) prefetch_l2(gn + v * vstep);
                 }
             }
+            // (PDL: everything above only read this op's inputs; the zero-fill kernel launched just before must be
+            // complete before the first RED -- a no-op when the kernel was launched in plain stream order)
+            pdl_wait();
             // ---- stage B': every footprint voxel gathers its weighted sum, then 2 REDs ------
             for (int idx = slot; idx < nvox; idx += vs) {
                 const int rr = (int)(((float)idx + 0.5f) * rnx), cx = idx - rr * nx, r = rlo + rr;
@@ -853,8 +856,19 @@ int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int
     return ROI3D_OK;
 }
 
+// The op's zero-fill as a kernel that lets its successor start early: the scatter kernel behind it is launched with
+// programmatic dependent launch, builds its tables and stages its first grads slice while the zeros are still being
+// written, and waits (griddepcontrol.wait) only before its first RED.
+__global__ void __launch_bounds__(256)
+zero_fill_kernel(float4 *__restrict__ p, size_t n4)
+{
+    pdl_trigger();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+}
+
 static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, const PyrParams *pyr, cudaStream_t stream)
+                                  float *grad_image, const PyrParams *pyr, cudaStream_t stream, bool zero_fill = false)
 {
     PlaneLaunch L;
     int V;
@@ -878,15 +892,24 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
         ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{});
+    if (zero_fill) {
+        const size_t n4 = (size_t)g.B * g.H * g.W * g.D * g.C / 4;
+        zero_fill_kernel<<<kNumSMs * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(grad_image), n4);
+        ROI3D_LAUNCH_CHECK();
+        ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
+                                        grad_image, PyrParams{}));
+    } else {
+        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{});
+    }
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
 
+// zero_fill: the launcher also performs the op's zero-fill of grad_image (as a kernel the scatter kernel overlaps with)
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream)
+                                  float *grad_image, cudaStream_t stream, bool zero_fill)
 {
-    return launch_grad_plane_impl(grads, boxes, box_ind, g, grad_image, nullptr, stream);
+    return launch_grad_plane_impl(grads, boxes, box_ind, g, grad_image, nullptr, stream, zero_fill);
 }
 
 // ---- fused PyramidROIAlign entry points (geometry g: B, C, n = B * R, crop; H/W/D = the largest level, for sizing) ----

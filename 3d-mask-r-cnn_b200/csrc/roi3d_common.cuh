@@ -177,7 +177,7 @@ int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int
 int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream);
+                                  float *grad_image, cudaStream_t stream, bool zero_fill = false);
 int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
                        const float *boxes, int rois_per_image, float imH, float imW, float imD,
                        int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream);
