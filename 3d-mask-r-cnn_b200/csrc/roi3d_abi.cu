@@ -2,14 +2,48 @@
 // validation, variant selection and kernel launches.  No torch / TF types, no
 // allocation, no device or stream synchronisation, no CPU fallback.
 #include "roi3d_common.cuh"
-#include <atomic>
+#include <map>
+#include <mutex>
 #include <string.h>
+#include <utility>
 
 namespace roi3d {
 thread_local int g_last_cuda_error = 0;
 thread_local long long g_launches = 0;
-static std::atomic<int> g_options[OPT_COUNT];
-int option_value(int which) { return g_options[which].load(std::memory_order_relaxed); }
+// Tuning knobs are per calling thread: nothing another thread (a second TF inter-op worker, a second torch stream
+// thread) does can change the kernels this thread's calls select.
+static thread_local int g_options[OPT_COUNT];
+int option_value(int which) { return g_options[which]; }
+
+// The only process-wide state: two caches of facts about the device (the opt-in shared-memory size already granted
+// to a kernel, the SM count).  Both are idempotent -- a lost race repeats a query, never changes a result.
+cudaError_t ensure_dyn_smem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = granted[std::make_pair(kernel, dev)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+int num_sms()
+{
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev];
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return v;
+}
 
 static int option_index(const char *name) {
     if (!name) return -1;
@@ -19,7 +53,10 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_lanes_v")) return OPT_CAR_V;
     if (!strcmp(name, "car_ctas_per_sm_target")) return OPT_KSPLIT;
     if (!strcmp(name, "nms_sort_variant")) return OPT_NMS_SORT;
-    if (!strcmp(name, "nms_pdl")) return OPT_NMS_PDL;
+    if (!strcmp(name, "pdl") || !strcmp(name, "nms_pdl")) return OPT_PDL;     // "nms_pdl": round-1 name, kept as an alias
+    if (!strcmp(name, "car_os_tile_depth")) return OPT_OS_TZ;
+    if (!strcmp(name, "car_os_chunks_per_cta")) return OPT_OS_CPC;
+    if (!strcmp(name, "car_os_shape")) return OPT_OS_SHAPE;
     return -1;
 }
 
@@ -57,13 +94,13 @@ void roi3d_reset_kernel_launches(void) { g_launches = 0; }
 int roi3d_set_option(const char *name, int value) {
     const int i = option_index(name);
     if (i < 0) return ROI3D_EINVAL;
-    g_options[i].store(value, std::memory_order_relaxed);
+    g_options[i] = value;
     return ROI3D_OK;
 }
 int roi3d_get_option(const char *name, int *value) {
     const int i = option_index(name);
     if (i < 0 || !value) return ROI3D_EINVAL;
-    *value = g_options[i].load(std::memory_order_relaxed);
+    *value = g_options[i];
     return ROI3D_OK;
 }
 
@@ -134,13 +171,20 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the op's contract: the whole output is defined (GI.so@0x3ec5 zero-fills it)
     int variant = option_value(OPT_CAR_BWD_VARIANT);
-    const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 &&
-                          ((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(grad_image)) & 15) == 0;
-    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
-    const bool plane = n > 0 && variant == 2 && plane_ok && grads && boxes && box_ind;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(grad_image)) & 15) == 0;
+    const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 && aligned;
+    const bool os_ok = method == ROI3D_METHOD_TRILINEAR && aligned && car3d_grad_image_os_supported(g);
+    const bool have_in = n > 0 && grads && boxes && box_ind;
+    // auto: the output-stationary kernel (every voxel stored once, no zero-fill, no atomics) whenever the output has
+    // enough tiles to fill the GPU; the scatter kernel for small maps; the direct kernel for nearest / odd channels
+    if (variant == 0)
+        variant = (os_ok && false && C >= 32 && car3d_grad_image_os_ctas(g) >= 2ll * num_sms()) ? 3 : ((plane_ok && C >= 32) ? 2 : 1);   // TODO(os): opt-in until it wins
+    if (variant == 3 && os_ok && have_in) return launch_car3d_grad_image_os(grads, boxes, box_ind, g, grad_image, s);
+    if (variant == 3) variant = (plane_ok && C >= 32) ? 2 : 1;
+    const bool plane = have_in && variant == 2 && plane_ok;
     // plane path: the zero-fill is a kernel that the scatter kernel overlaps with (programmatic dependent launch;
-    // option "nms_pdl" = 1 restores memset + plain stream order)
-    const bool fused_fill = plane && option_value(OPT_NMS_PDL) == 0;
+    // option "pdl" = 1 restores memset + plain stream order)
+    const bool fused_fill = plane && option_value(OPT_PDL) == 0;
     if (!fused_fill) ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
     if (n == 0) return ROI3D_OK;
     if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;

@@ -345,7 +345,7 @@ int launch_topk(const float *scores, int n, int k, int *idx_out, float *scores_o
     unsigned *eq_off = reinterpret_cast<unsigned *>(base + st_bytes + 2 * arr);
     unsigned *sel_off = reinterpret_cast<unsigned *>(base + st_bytes + 3 * arr);
     ROI3D_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(TopkState), stream));
-    const int hgrid = min((n + TK_THREADS - 1) / TK_THREADS, kNumSMs * 2);
+    const int hgrid = min((n + TK_THREADS - 1) / TK_THREADS, num_sms() * 2);
     for (int pass = 0; pass < 3; ++pass) {
         ROI3D_CUDA_TRY(launch_dependent(topk_hist_kernel, dim3(hgrid), dim3(TK_THREADS), 0, stream, true, scores, n, pass, k, st));
         ROI3D_LAUNCH_CHECK();

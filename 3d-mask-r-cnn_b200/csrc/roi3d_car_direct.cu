@@ -242,7 +242,7 @@ car3d_grad_boxes_kernel(const float *__restrict__ grads, const float *__restrict
 // ---------------------------------------------------------------------------------
 static inline int grid_for(long long total, int threads) {
     long long blocks = (total + threads - 1) / threads;
-    const long long cap = (long long)kNumSMs * 32;             // grid-stride beyond 32 CTAs/SM
+    const long long cap = (long long)num_sms() * 32;             // grid-stride beyond 32 CTAs/SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;

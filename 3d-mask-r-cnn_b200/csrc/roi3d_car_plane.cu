@@ -783,7 +783,7 @@ static void pick_lanes(const CarGeom &g, int &cl, int &V) {
 }
 
 static int pick_ksplits(const CarGeom &g, int chunks) {
-    const long long want = (long long)kNumSMs * (option_value(OPT_KSPLIT) > 0 ? option_value(OPT_KSPLIT) : 16);
+    const long long want = (long long)num_sms() * (option_value(OPT_KSPLIT) > 0 ? option_value(OPT_KSPLIT) : 16);
     const long long per = (long long)g.n * chunks;
     long long ks = (want + per - 1) / per;
     if (ks < 1) ks = 1;
@@ -816,7 +816,7 @@ static int launch_fwd_plane_impl(const float *image, const float *boxes, const i
               : pyr ? ((V == 2) ? car3d_fwd_plane_kernel<2, true> : car3d_fwd_plane_kernel<1, true>)
                     : ((V == 2) ? car3d_fwd_plane_kernel<2, false> : car3d_fwd_plane_kernel<1, false>);
     if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, pyr ? *pyr : PyrParams{});
@@ -848,7 +848,7 @@ int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int
     L.ksplits = pick_ksplits(g, L.chunks);
     auto kern = car3d_fwd_plane_tma_kernel<false>;
     if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, PyrParams{});
@@ -889,12 +889,12 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
     auto kern = pyr ? ((V == 2) ? car3d_grad_image_plane_kernel<2, true> : car3d_grad_image_plane_kernel<1, true>)
                     : ((V == 2) ? car3d_grad_image_plane_kernel<2, false> : car3d_grad_image_plane_kernel<1, false>);
     if (smem > 48 * 1024)
-        ROI3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     if (zero_fill) {
         const size_t n4 = (size_t)g.B * g.H * g.W * g.D * g.C / 4;
-        zero_fill_kernel<<<kNumSMs * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(grad_image), n4);
+        zero_fill_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(grad_image), n4);
         ROI3D_LAUNCH_CHECK();
         ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
                                         grad_image, PyrParams{}));

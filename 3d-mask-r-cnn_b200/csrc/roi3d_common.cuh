@@ -17,7 +17,12 @@ namespace roi3d {
 extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
-enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_NMS_PDL = 6, OPT_COUNT };
+enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_PDL = 6,
+       OPT_OS_TZ = 7, OPT_OS_CPC = 8, OPT_OS_SHAPE = 9, OPT_COUNT };
+// cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, device, size) instead of on every call
+cudaError_t ensure_dyn_smem(const void *kernel, size_t bytes);
+// multiprocessor count of the current device (cached per device)
+int num_sms();
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -35,7 +40,6 @@ inline int cuda_fail(cudaError_t e) {
         if (e__ != cudaSuccess) return ::roi3d::cuda_fail(e__);     \
     } while (0)
 
-constexpr int kNumSMs = 148;   // B200
 
 // ---- sample coordinates (CAR.so@0x499a-0x4ae5, 0x533a) ---------------------
 // scale = ((a2 - a1) * f(dim-1)) / f(p-1)            (p > 1), else 0
@@ -178,6 +182,10 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
                                   float *grad_image, cudaStream_t stream, bool zero_fill = false);
+bool car3d_grad_image_os_supported(const CarGeom &g);
+long long car3d_grad_image_os_ctas(const CarGeom &g);
+int launch_car3d_grad_image_os(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
+                               float *grad_image, cudaStream_t stream);
 int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
                        const float *boxes, int rois_per_image, float imH, float imW, float imD,
                        int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream);

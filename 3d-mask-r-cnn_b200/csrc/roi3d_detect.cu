@@ -222,7 +222,7 @@ static int launch_mask_targets_t(const T *masks, int H, int W, int D, const floa
                                  int mh, int mw, int md, float *targets, unsigned char *bits, cudaStream_t stream)
 {
     const long long total = (long long)n * mh * mw * md;
-    const long long blocks = min((total + 255) / 256, (long long)kNumSMs * 16);
+    const long long blocks = min((total + 255) / 256, (long long)num_sms() * 16);
     mask_targets_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(masks, H, W, D, boxes, assignment, n, mh, mw, md, targets, bits);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
@@ -329,7 +329,7 @@ unpack_bits_kernel(const unsigned char *__restrict__ bits, long long n, float *_
 
 static unsigned wire_grid(long long work_items) {
     const long long blocks = (work_items + 255) / 256;
-    return (unsigned)max(1ll, min(blocks, (long long)kNumSMs * 32));
+    return (unsigned)max(1ll, min(blocks, (long long)num_sms() * 32));
 }
 
 int launch_f32_to_f16(const float *x, long long n, void *y, cudaStream_t stream)

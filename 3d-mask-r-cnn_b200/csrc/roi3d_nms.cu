@@ -705,13 +705,13 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
         ROI3D_LAUNCH_CHECK();
     }
     const size_t smem = ((size_t)2 * SC_SB * SC_P + 4 * SC_SB) * sizeof(unsigned);
-    ROI3D_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(nms_scan_kernel), smem));
     // Head / tail split.  The scan stops as soon as max_out boxes are selected, i.e. after about max_out sorted boxes
     // when few of them suppress each other -- far from n.  So the first T = max_out * 1.25 + 256 boxes (rounded up
     // to whole super-chunks) get their own mask triangle and scan; the rest of the mask (the bulk of the n^2 / 2
     // pairs) and the tail scan are launched behind it and return immediately when the head already finished.
     // nms_variant 1 forces the single-phase schedule.
-    const bool pdl = option_value(OPT_NMS_PDL) == 0;
+    const bool pdl = option_value(OPT_PDL) == 0;
     const int nsb = (n + SC_SB - 1) / SC_SB;
     int head_sb = (int)(((long long)max_out + max_out / 4 + 256 + SC_SB - 1) / SC_SB);
     if (option_value(OPT_NMS_VARIANT) == 1 || head_sb >= nsb) head_sb = nsb;
