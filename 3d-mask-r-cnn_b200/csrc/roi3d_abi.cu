@@ -55,8 +55,10 @@ static int option_index(const char *name) {
     if (!strcmp(name, "nms_sort_variant")) return OPT_NMS_SORT;
     if (!strcmp(name, "pdl") || !strcmp(name, "nms_pdl")) return OPT_PDL;     // "nms_pdl": round-1 name, kept as an alias
     if (!strcmp(name, "car_os_tile_depth")) return OPT_OS_TZ;
-    if (!strcmp(name, "car_os_chunks_per_cta")) return OPT_OS_CPC;
-    if (!strcmp(name, "car_os_shape")) return OPT_OS_SHAPE;
+    if (!strcmp(name, "car_os_ring_stages")) return OPT_OS_STAGES;
+    if (!strcmp(name, "car_os_stage_kib")) return OPT_OS_STAGE_KIB;
+    if (!strcmp(name, "car_os_debug")) return OPT_OS_DEBUG;
+    if (!strcmp(name, "car_bwd_image_split")) return OPT_BWD_SPLIT;
     return -1;
 }
 
@@ -175,10 +177,10 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 && aligned;
     const bool os_ok = method == ROI3D_METHOD_TRILINEAR && aligned && car3d_grad_image_os_supported(g);
     const bool have_in = n > 0 && grads && boxes && box_ind;
-    // auto: the output-stationary kernel (every voxel stored once, no zero-fill, no atomics) whenever the output has
-    // enough tiles to fill the GPU; the scatter kernel for small maps; the direct kernel for nearest / odd channels
-    if (variant == 0)
-        variant = (os_ok && false && C >= 32 && car3d_grad_image_os_ctas(g) >= 2ll * num_sms()) ? 3 : ((plane_ok && C >= 32) ? 2 : 1);   // TODO(os): opt-in until it wins
+    // auto: the plane-staged RED scatter.  The output-stationary kernel (variant 3: every voxel stored once, no
+    // zero-fill, no atomics, deterministic; DRAM traffic 1.03 vs 1.80 GB at cfg2 14^3) is opt-in: it is latency-bound on
+    // per-(box, tile) bookkeeping and measures 0.55-0.64 ms against 0.39 ms (profiles/r2_os_grad_image_ncu.txt)
+    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
     if (variant == 3 && os_ok && have_in) return launch_car3d_grad_image_os(grads, boxes, box_ind, g, grad_image, s);
     if (variant == 3) variant = (plane_ok && C >= 32) ? 2 : 1;
     const bool plane = have_in && variant == 2 && plane_ok;

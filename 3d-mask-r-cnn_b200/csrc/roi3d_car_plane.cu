@@ -606,7 +606,7 @@ template <int V, bool PYR>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
-                              float *__restrict__ grad_image, const PyrParams P)
+                              float *__restrict__ grad_image, const PyrParams P, const int only_image)
 {
     constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -619,6 +619,8 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     const int chunk = bid % L.chunks; bid /= L.chunks;
     const int ks = bid % L.ksplits;
     const int b = bid / L.ksplits;
+    // per-image launches (the output slice of one image stays L2-resident between its zero-fill and its REDs)
+    if (!PYR && only_image >= 0 && __ldg(box_ind + b) != only_image) return;
     __shared__ int s_level;
     if constexpr (PYR) {
         if (threadIdx.x == 0) {
@@ -893,13 +895,22 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     if (zero_fill) {
-        const size_t n4 = (size_t)g.B * g.H * g.W * g.D * g.C / 4;
-        zero_fill_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(grad_image), n4);
-        ROI3D_LAUNCH_CHECK();
-        ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
-                                        grad_image, PyrParams{}));
+        // Opt-in experiment ("car_bwd_image_split" = 1): zero-fill and scatter image by image, so that the REDs find the zeros
+        // still in L2 instead of fetching them back from DRAM.  Measured at cfg2 (profiles/split_experiment.py): 0.438 vs
+        // 0.390 ms at 14^3, 0.153 vs 0.142 ms at 7^3 -- the half-empty grids cost more than the traffic saves.  Off by default.
+        const size_t per_image = (size_t)g.H * g.W * g.D * g.C * sizeof(float);
+        const bool split = option_value(OPT_BWD_SPLIT) == 1 && g.B > 1;
+        for (int img = 0; img < (split ? g.B : 1); ++img) {
+            const size_t n4 = (split ? per_image : per_image * g.B) / 16;
+            float *dst = grad_image + (split ? (size_t)img * (per_image / 4) : 0);
+            zero_fill_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
+            ROI3D_LAUNCH_CHECK();
+            ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
+                                            grad_image, PyrParams{}, split ? img : -1));
+            if (img + 1 < (split ? g.B : 1)) ROI3D_LAUNCH_CHECK();
+        }
     } else {
-        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{});
+        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, -1);
     }
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;

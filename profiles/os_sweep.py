@@ -36,20 +36,16 @@ for name, B, R, crops in cases:
         print("%s crop %2d scatter          %.4f ms  alg %5.0f GB/s  compulsory %5.0f GB/s" % (name, c, t2, bb / t2 / 1e6, comp / t2 / 1e6))
         rb.set_option("car_bwd_variant", 3)
         best = None
-        for shape_id in (0, 1, 2):
-            for V in (1, 2):
-                for tz in (8, 16):
-                    for cpc in (1, 4):
-                        rb.set_option("car_os_shape", shape_id); rb.set_option("car_lanes_v", V)
-                        rb.set_option("car_os_tile_depth", tz); rb.set_option("car_os_chunks_per_cta", cpc)
-                        try:
-                            t3 = timeit(call)
-                        except Exception as e:
-                            print("  shape%d V%d tz%2d cpc%d failed: %s" % (shape_id, V, tz, cpc, e)); continue
-                        err = float((out - ref).abs().max() / ref.abs().max())
-                        print("%s crop %2d os shape%d V%d tz%2d cpc%d  %.4f ms  alg %5.0f GB/s  compulsory %5.0f GB/s  maxerr %.1e" %
-                              (name, c, shape_id, V, tz, cpc, t3, bb / t3 / 1e6, comp / t3 / 1e6, err))
-                        if best is None or t3 < best[0]: best = (t3, shape_id, V, tz, cpc)
-        print("%s crop %2d BEST os %.4f ms shape%d V%d tz%d cpc%d (scatter %.4f)" % ((name, c) + best + (t2,)))
-        for k in ("car_lanes_v", "car_os_tile_depth", "car_os_chunks_per_cta", "car_os_shape"): rb.set_option(k, 0)
+        for tz in (8, 16, 32):
+            rb.set_option("car_os_tile_depth", tz)
+            try:
+                t3 = timeit(call)
+            except Exception as e:
+                print("  tz%2d failed: %s" % (tz, e)); continue
+            err = float((out - ref).abs().max() / ref.abs().max())
+            print("%s crop %2d os tz%2d  %.4f ms  alg %5.0f GB/s  compulsory %5.0f GB/s  maxerr %.1e" %
+                  (name, c, tz, t3, bb / t3 / 1e6, comp / t3 / 1e6, err))
+            if best is None or t3 < best[0]: best = (t3, tz)
+        print("%s crop %2d BEST os %.4f ms tz%d (scatter %.4f)" % ((name, c) + best + (t2,)))
+        for k in ("car_os_tile_depth",): rb.set_option(k, 0)
         del g
