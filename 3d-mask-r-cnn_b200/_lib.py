@@ -122,7 +122,7 @@ def _declare(lib):
     lib.roi3d_refine_detections_workspace_bytes.restype = sz
     lib.roi3d_refine_detections_workspace_bytes.argtypes = [i, i, i]
     lib.roi3d_refine_detections.restype = i
-    lib.roi3d_refine_detections.argtypes = [vp, vp, vp, i, i, i, vp, vp, f, f, i, vp, vp, vp, sz, vp]
+    lib.roi3d_refine_detections.argtypes = [vp, vp, vp, i, i, i, vp, vp, f, f, i, i, vp, vp, vp, sz, vp]
     lib.roi3d_mask_targets.restype = i
     lib.roi3d_mask_targets.argtypes = [vp, i, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp]
     for name in ("roi3d_pack_f16", "roi3d_unpack_f16", "roi3d_pack_bits", "roi3d_unpack_bits"):

@@ -251,9 +251,10 @@ size_t roi3d_refine_detections_workspace_bytes(int images, int rois_per_image, i
 
 int roi3d_refine_detections(const float *rois, const float *probs, const float *deltas, int images, int rois_per_image,
                             int num_classes, const float image_shape[3], const float std_dev[6], float min_confidence,
-                            float nms_threshold, int max_instances, float *detections, int *det_count, void *workspace,
-                            size_t workspace_bytes, roi3d_stream_t stream)
+                            float nms_threshold, int nms_mode, int max_instances, float *detections, int *det_count,
+                            void *workspace, size_t workspace_bytes, roi3d_stream_t stream)
 {
+    if (nms_mode != ROI3D_NMS_REFERENCE_2D && nms_mode != ROI3D_NMS_3D) return ROI3D_EINVAL;
     if (images < 0 || rois_per_image < 0 || num_classes < 2 || max_instances < 0 || !image_shape || !std_dev) return ROI3D_EINVAL;
     if (!(nms_threshold >= 0.0f && nms_threshold <= 1.0f)) return ROI3D_EINVAL;
     if (!(image_shape[0] > 0.0f && image_shape[1] > 0.0f && image_shape[2] > 0.0f)) return ROI3D_EINVAL;
@@ -261,7 +262,7 @@ int roi3d_refine_detections(const float *rois, const float *probs, const float *
     if (!detections || (rois_per_image > 0 && (!rois || !probs || !deltas))) return ROI3D_EINVAL;
     if ((long long)images * max_instances * 8 > 0x7fffffffll || (long long)images * rois_per_image > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     return launch_refine_detections(rois, probs, deltas, images, rois_per_image, num_classes, image_shape, std_dev,
-                                    min_confidence, nms_threshold, max_instances, detections, det_count, workspace,
+                                    min_confidence, nms_threshold, nms_mode, max_instances, detections, det_count, workspace,
                                     workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

@@ -90,11 +90,13 @@ car3d_fwd_direct_kernel(const float *__restrict__ image, const float *__restrict
         const Sample sx = make_sample(__ldg(box + 1), __ldg(box + 4), g.W, g.pw, x);
         const Sample sz = make_sample(__ldg(box + 2), __ldg(box + 5), g.D, g.pd, z);
         float *out = crops + idx * VEC;
-        if (!(sy.valid && sx.valid && sz.valid)) {
+        const int bimg = __ldg(box_index + b);
+        // a box_index outside [0, B) reads nothing: the crop is the extrapolation value (the reference would read out of bounds)
+        if (!(sy.valid && sx.valid && sz.valid) || (unsigned)bimg >= (unsigned)g.B) {
             st(out, splat<VEC>(ext));
             continue;
         }
-        const float *img = image + (long long)__ldg(box_index + b) * g.H * sH + c;
+        const float *img = image + (long long)bimg * g.H * sH + c;
         if (method == ROI3D_METHOD_TRILINEAR) {
             const float *pt = img + sy.i0 * sH, *pb = img + sy.i1 * sH;
             const long long ol = sx.i0 * sW, orr = sx.i1 * sW, of = sz.i0 * sD, oc = sz.i1 * sD;
@@ -138,9 +140,10 @@ car3d_grad_image_direct_kernel(const float *__restrict__ grads, const float *__r
         const Sample sy = make_sample(__ldg(box + 0), __ldg(box + 3), g.H, g.ph, y);
         const Sample sx = make_sample(__ldg(box + 1), __ldg(box + 4), g.W, g.pw, x);
         const Sample sz = make_sample(__ldg(box + 2), __ldg(box + 5), g.D, g.pd, z);
-        if (!(sy.valid && sx.valid && sz.valid)) continue;
+        const int bimg = __ldg(box_ind + b);
+        if (!(sy.valid && sx.valid && sz.valid) || (unsigned)bimg >= (unsigned)g.B) continue;   // out-of-range box_ind: nothing is scattered
         const V gv = ld<VEC>(grads + idx * VEC);
-        float *img = grad_image + (long long)__ldg(box_ind + b) * g.H * sH + c;
+        float *img = grad_image + (long long)bimg * g.H * sH + c;
         if (method == ROI3D_METHOD_TRILINEAR) {
             const float wt = __fsub_rn(1.0f, sy.t), wb = sy.t;
             const float wl = __fsub_rn(1.0f, sx.t), wr = sx.t;
@@ -186,10 +189,12 @@ car3d_grad_boxes_kernel(const float *__restrict__ grads, const float *__restrict
     const float hs = (g.ph > 1) ? __fmul_rn(__fsub_rn(y2, y1), rh) : 0.0f;
     const float ws = (g.pw > 1) ? __fmul_rn(__fsub_rn(x2, x1), rw) : 0.0f;
     const float ds = (g.pd > 1) ? __fmul_rn(__fsub_rn(z2, y1), rh) : 0.0f;
-    const float *img = image + (long long)__ldg(box_ind + b) * g.H * sH;
+    const int bimg = __ldg(box_ind + b);
+    const float *img = image + (long long)bimg * g.H * sH;
     const float *gb = grads + (long long)b * g.ph * g.pw * g.pd * g.C;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long per_box = (long long)g.ph * g.pw * g.pd * g.C;
+    // a box_ind outside [0, B) reads nothing: its row of grad_boxes is zero
+    const long long per_box = ((unsigned)bimg < (unsigned)g.B) ? (long long)g.ph * g.pw * g.pd * g.C : 0;
     for (long long e = threadIdx.x; e < per_box; e += blockDim.x) {
         const int c = (int)(e % g.C);
         long long r = e / g.C;

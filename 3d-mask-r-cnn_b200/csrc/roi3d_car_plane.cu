@@ -27,6 +27,8 @@
 // and issues two vector REDs (floor z, ceil z) instead of 8 per grads element.
 #include "roi3d_common.cuh"
 #include <type_traits>
+#include <math.h>
+#include <string.h>
 
 namespace roi3d {
 
@@ -182,11 +184,38 @@ struct PyrParams {
     int H[4], W[4], D[4];       // level shapes [B, H_l, W_l, D_l, C]
     float imH, imW, imD;        // image_shape from image_meta (routing and the z min-size rule)
     int rois_per_image;         // boxes are [B, R, 6]; box_index = roi / R
+    float lt[3];                // smallest normalized box volume routed to level 3 / 4 / 5 (host: pyr_level_thresholds)
 };
 
 struct PyrRoute { float box[6]; int level; };
 
-// tf.clip_by_value, min sizes, level = clamp(4 + round(log2(cbrt(h*w*d) / (224 / cbrt(H*W*D)))), 2, 5) in fp32
+// The level expression of PyramidROIAlign.call (core/models.py:637-649), fp32 like the TF graph:
+//   level = clamp(4 + round(log2(cbrt(h*w*d) / (224 / cbrt(H*W*D)))), 2, 5)
+// It depends on the box only through vol = h*w*d and is monotonic in it, so the host turns it into three volume
+// thresholds once per call (bisection over the fp32 values of vol, same formula) and a CTA routes its box with three
+// compares instead of two powf and two logf on its critical path (round 1: ~0.4 us per CTA before anything else could
+// start).  As before, a box whose expression lies within an ulp of x.5 may land on the other side than with another libm.
+static inline int pyr_level_of(float vol, float imH, float imW, float imD) {
+    const float area = (imH * imW) * imD;
+    const float ratio = powf(vol, 1.0f / 3.0f) / (224.0f / powf(area, 1.0f / 3.0f));
+    const float lvl = logf(ratio) / logf(2.0f);
+    const int k = 4 + (int)nearbyintf(lvl);                   // tf.round: half to even
+    return k < 2 ? 2 : (k > 5 ? 5 : k);
+}
+static void pyr_level_thresholds(float imH, float imW, float imD, float lt[3]) {
+    for (int target = 3; target <= 5; ++target) {
+        uint32_t lo = 0x00800000u, hi = 0x7f000000u;          // smallest normal .. huge: vol > 0 always (min sizes)
+        while (lo < hi) {                                      // smallest vol whose level is >= target
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float v;
+            memcpy(&v, &mid, 4);
+            if (pyr_level_of(v, imH, imW, imD) >= target) hi = mid; else lo = mid + 1;
+        }
+        memcpy(&lt[target - 3], &lo, 4);
+    }
+}
+
+// tf.clip_by_value + min sizes (core/models.py:615-632), then the level from the host's thresholds
 __device__ __forceinline__ PyrRoute pyr_route(const float *b6, const PyrParams &P) {
     PyrRoute r;
     float y1 = fminf(fmaxf(b6[0], 0.f), 1.f), x1 = fminf(fmaxf(b6[1], 0.f), 1.f), z1 = fminf(fmaxf(b6[2], 0.f), 1.f);
@@ -196,11 +225,17 @@ __device__ __forceinline__ PyrRoute pyr_route(const float *b6, const PyrParams &
     z2 = fmaxf(z2, __fadd_rn(z1, __fdiv_rn(1.0f, fmaxf(P.imD, 1.0f))));
     r.box[0] = y1; r.box[1] = x1; r.box[2] = z1; r.box[3] = y2; r.box[4] = x2; r.box[5] = z2;
     const float vol = __fmul_rn(__fmul_rn(__fsub_rn(y2, y1), __fsub_rn(x2, x1)), __fsub_rn(z2, z1));
-    const float area = __fmul_rn(__fmul_rn(P.imH, P.imW), P.imD);
-    const float ratio = __fdiv_rn(powf(vol, 1.0f / 3.0f), __fdiv_rn(224.0f, powf(area, 1.0f / 3.0f)));
-    const float lvl = __fdiv_rn(logf(ratio), logf(2.0f));
-    r.level = min(5, max(2, 4 + (int)rintf(lvl)));
+    r.level = 2 + (vol >= P.lt[0]) + (vol >= P.lt[1]) + (vol >= P.lt[2]);
     return r;
+}
+
+// level l of the pyramid parameters with constant indices only (a run-time index into a kernel parameter array makes
+// the compiler copy the struct to local memory: round 1's PYR kernels carried a 96-byte stack frame for it)
+__device__ __forceinline__ void pyr_level(const PyrParams &P, int lv, int &H, int &W, int &D, const float *&img) {
+    H = lv == 0 ? P.H[0] : (lv == 1 ? P.H[1] : (lv == 2 ? P.H[2] : P.H[3]));
+    W = lv == 0 ? P.W[0] : (lv == 1 ? P.W[1] : (lv == 2 ? P.W[2] : P.W[3]));
+    D = lv == 0 ? P.D[0] : (lv == 1 ? P.D[1] : (lv == 2 ? P.D[2] : P.D[3]));
+    img = lv == 0 ? P.image[0] : (lv == 1 ? P.image[1] : (lv == 2 ? P.image[2] : P.image[3]));
 }
 
 __device__ __forceinline__ float4 scrub4(const float4 v) {       // tf.where(is_finite(x), x, 0), core/models.py:683
@@ -247,8 +282,9 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
         }
         __syncthreads();
         const int lv = s_level;
-        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
-        image = P.image[lv];
+        const float *lim;
+        pyr_level(P, lv, g.H, g.W, g.D, lim);
+        image = lim;
     } else {
         if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
         __syncthreads();
@@ -266,6 +302,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
+    const bool bad_img = (unsigned)bimg >= (unsigned)g.B;     // out-of-range box_index: the whole crop extrapolates, nothing is read
     const float *img = image + (long long)bimg * g.H * sH + c4 * 4;
     OutT *crop = static_cast<OutT *>(crops) + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float4 ext4 = make_float4(ext, ext, ext, ext);
@@ -313,7 +350,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
         for (int k = k0; k < k1; ++k) {
             const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
             OutT *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
-            if (axis_invalid(in_z, g.D) || nvox == 0) {       // uniform: every output of this (tile, k) extrapolates
+            if (axis_invalid(in_z, g.D) || nvox == 0 || bad_img) {   // uniform: every output of this (tile, k) extrapolates
                 for (int idx = slot; idx < nout; idx += vs, o += ostride) {
 #pragma unroll
                     for (int v = 0; v < V; ++v)
@@ -440,8 +477,9 @@ car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restr
         }
         __syncthreads();
         const int lv = s_level;
-        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
-        image = P.image[lv];
+        const float *lim;
+        pyr_level(P, lv, g.H, g.W, g.D, lim);
+        image = lim;
     } else {
         if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
         __syncthreads();
@@ -460,6 +498,7 @@ car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restr
     const unsigned rowbytes = (unsigned)min(cl, g.C / 4 - chunk * cl) * 16;  // bytes of this chunk actually present
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
+    const bool bad_img = (unsigned)bimg >= (unsigned)g.B;
     const float *img_chunk = image + (long long)bimg * g.H * sH + chunk * cl * 4;   // lane-independent: TMA source
     float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float4 ext4 = make_float4(ext, ext, ext, ext);
@@ -514,7 +553,7 @@ car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restr
                 }
             }
         };
-        auto zvalid = [&](int k) { return k < k1 && nvox > 0 && !axis_invalid(axis_coord(z1, z2, g.D, g.pd, k, zscale), g.D); };
+        auto zvalid = [&](int k) { return k < k1 && nvox > 0 && !bad_img && !axis_invalid(axis_coord(z1, z2, g.D, g.pd, k, zscale), g.D); };
 
         int kfirst = k0;
         while (kfirst < k1 && !zvalid(kfirst)) ++kfirst;
@@ -634,8 +673,9 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
         }
         __syncthreads();
         const int lv = s_level;
-        g.H = P.H[lv]; g.W = P.W[lv]; g.D = P.D[lv];
-        grad_image = const_cast<float *>(P.image[lv]);
+        const float *gim;
+        pyr_level(P, lv, g.H, g.W, g.D, gim);
+        grad_image = const_cast<float *>(gim);
     } else {
         if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
         __syncthreads();
@@ -655,6 +695,7 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
     const long long sW = (long long)g.D * g.C, sH = (long long)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_ind + b);
+    if ((unsigned)bimg >= (unsigned)g.B) return;             // out-of-range box_ind (CTA-uniform): nothing is scattered
     float *img = grad_image + (long long)bimg * g.H * sH + c4 * 4;
     const float *gcrop = grads + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
     const float z1 = S.box[2], z2 = S.box[5];
@@ -869,8 +910,25 @@ zero_fill_kernel(float4 *__restrict__ p, size_t n4)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
 }
 
+struct Fill4 { float4 *p[4]; size_t n4[4]; };
+// the fused PyramidROIAlign backward's zero-fill of the four grad maps in ONE kernel that triggers its successor at once
+__global__ void __launch_bounds__(256)
+zero_fill4_kernel(const Fill4 f)
+{
+    pdl_trigger();
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float4 *p = f.p[r];
+        const size_t n4 = f.n4[r];
+        for (size_t i = t0; i < n4; i += stride) p[i] = z;
+    }
+}
+
 static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, const PyrParams *pyr, cudaStream_t stream, bool zero_fill = false)
+                                  float *grad_image, const PyrParams *pyr, cudaStream_t stream, bool zero_fill = false,
+                                  bool pdl_after_fill = false)
 {
     PlaneLaunch L;
     int V;
@@ -909,6 +967,9 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
                                             grad_image, PyrParams{}, split ? img : -1));
             if (img + 1 < (split ? g.B : 1)) ROI3D_LAUNCH_CHECK();
         }
+    } else if (pdl_after_fill) {                               // the caller has just enqueued the zero-fill kernel
+        ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
+                                        grad_image, pyr ? *pyr : PyrParams{}, -1));
     } else {
         kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, -1);
     }
@@ -931,6 +992,7 @@ int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W
     PyrParams P;
     for (int l = 0; l < 4; ++l) { P.image[l] = images[l]; P.H[l] = H[l]; P.W[l] = W[l]; P.D[l] = D[l]; }
     P.imH = imH; P.imW = imW; P.imD = imD; P.rois_per_image = rois_per_image;
+    pyr_level_thresholds(imH, imW, imD, P.lt);
     int wmax = 1;
     for (int l = 0; l < 4; ++l) wmax = max(wmax, W[l]);
     const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
@@ -942,16 +1004,23 @@ int launch_pyramid_grad(const float *grads, float *const grad_images[4], const i
                         int ph, int pw, int pd, cudaStream_t stream)
 {
     PyrParams P;
+    Fill4 f;
     for (int l = 0; l < 4; ++l) {
         P.image[l] = grad_images[l]; P.H[l] = H[l]; P.W[l] = W[l]; P.D[l] = D[l];
-        ROI3D_CUDA_TRY(cudaMemsetAsync(grad_images[l], 0, sizeof(float) * (size_t)B * H[l] * W[l] * D[l] * C, stream));
+        f.p[l] = reinterpret_cast<float4 *>(grad_images[l]);
+        f.n4[l] = (size_t)B * H[l] * W[l] * D[l] * C / 4;
     }
     P.imH = imH; P.imW = imW; P.imD = imD; P.rois_per_image = rois_per_image;
+    pyr_level_thresholds(imH, imW, imD, P.lt);
     int wmax = 1;
     for (int l = 0; l < 4; ++l) wmax = max(wmax, W[l]);
     const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
+    // one zero-fill kernel for the four maps; the scatter kernel behind it is launched with programmatic dependent
+    // launch and waits (griddepcontrol.wait) only before its first RED (option "pdl" = 1: plain stream order)
+    zero_fill4_kernel<<<num_sms() * 8, 256, 0, stream>>>(f);
+    ROI3D_LAUNCH_CHECK();
     if (g.n == 0) return ROI3D_OK;
-    return launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream);
+    return launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream, false, option_value(OPT_PDL) == 0);
 }
 
 }  // namespace roi3d

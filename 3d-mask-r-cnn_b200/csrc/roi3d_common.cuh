@@ -203,8 +203,8 @@ size_t nms3d_workspace_bytes(int n, int segments);
 size_t refine_detections_workspace_bytes(int images, int rois, int max_inst);
 int launch_refine_detections(const float *rois, const float *probs, const float *deltas, int images, int rois_per_image,
                              int num_classes, const float image_shape[3], const float std_dev[6], float min_conf,
-                             float nms_thr, int max_inst, float *detections, int *det_count, void *ws, size_t ws_bytes,
-                             cudaStream_t stream);
+                             float nms_thr, int nms_mode, int max_inst, float *detections, int *det_count, void *ws,
+                             size_t ws_bytes, cudaStream_t stream);
 int launch_mask_targets(const void *masks, int mask_dtype, int H, int W, int D, const float *boxes, const int *assignment,
                         int n, int mh, int mw, int md, float *targets, unsigned char *bits, cudaStream_t stream);
 int launch_f32_to_f16(const float *x, long long n, void *y, cudaStream_t stream);

@@ -2,8 +2,12 @@
 //
 //   refine_detections : DetectionLayer / refine_detections_graph (core/models.py:1415-1524) for a whole batch in one
 //                       set of launches: class-1 score + deltas, confidence filter, apply_box_deltas_3d_graph in pixel
-//                       space (core/utils.py:412-464), clip to the image, min sizes, NMS (the 3-D op, as row f3 asks,
-//                       instead of the fork's 2-D tf.image NMS on y/x), score order, normalise, zero-pad.  Filters are
+//                       space (core/utils.py:412-464), clip to the image, min sizes, NMS, score order, normalise,
+//                       zero-pad.  NMS modes: ROI3D_NMS_REFERENCE_2D (default) = what the fork's graph does, the 2-D
+//                       tf.image.non_max_suppression on the (y, x) projection, suppressing on IoU > thr (:1496-1501),
+//                       run on the 3-D kernels with every box given z = [0, 1] (IoU3D == IoU2D bit for bit) and the
+//                       threshold moved one ulp up (iou > t  <=>  iou >= nextafter(t)); ROI3D_NMS_3D = the 3-D op with
+//                       its own >= rule, the upstream design row f3 asks for (opt-in).  Filters are
 //                       folded into the NMS candidate rule (score := -FLT_MAX), so nothing is compacted and no count
 //                       ever travels to the host.
 //   mask_targets      : detection_targets_graph._get_masks (core/models.py:972-1005): CropAndResize3D of the assigned
@@ -16,6 +20,7 @@
 #include "roi3d_common.cuh"
 #include <cuda_fp16.h>
 #include <cfloat>
+#include <math.h>
 
 namespace roi3d {
 
@@ -34,7 +39,8 @@ __device__ __forceinline__ float clip_rn(float v, float lo, float hi) { return f
 __global__ void __launch_bounds__(256)
 refine_decode_kernel(const float *__restrict__ rois, const float *__restrict__ probs, const float *__restrict__ deltas,
                      int total, int rois_per_image, int images, int num_classes, RefineParams P,
-                     float *__restrict__ boxes_px, float *__restrict__ scores, int *__restrict__ seg_offsets)
+                     float *__restrict__ boxes_px, float *__restrict__ boxes_nms, float *__restrict__ scores,
+                     int *__restrict__ seg_offsets)
 {
     pdl_wait();                                                // see roi3d_common.cuh: programmatic dependent launch
     pdl_trigger();
@@ -67,6 +73,10 @@ refine_decode_kernel(const float *__restrict__ rois, const float *__restrict__ p
     float *bo = boxes_px + (size_t)i * 6;
 #pragma unroll
     for (int q = 0; q < 6; ++q) bo[q] = o[q];
+    if (boxes_nms) {                                                          // reference mode: NMS sees the (y, x) projection
+        float *bn = boxes_nms + (size_t)i * 6;
+        bn[0] = o[0]; bn[1] = o[1]; bn[2] = 0.0f; bn[3] = o[3]; bn[4] = o[4]; bn[5] = 1.0f;
+    }
     scores[i] = ok ? score : -FLT_MAX;                                        // not a candidate for the NMS op
 }
 
@@ -91,13 +101,14 @@ refine_gather_kernel(const float *__restrict__ boxes_px, const float *__restrict
     det[t] = v;
 }
 
-struct RefineLayout { size_t boxes, scores, offs, keep, count, nms, total; };
+struct RefineLayout { size_t boxes, boxes2d, scores, offs, keep, count, nms, total; };
 static size_t up256(size_t v) { return (v + 255) & ~size_t(255); }
 static RefineLayout refine_layout(int images, int rois, int max_inst) {
     RefineLayout L;
     size_t off = 0;
     const size_t total = (size_t)images * rois;
     L.boxes = off; off += up256(total * 6 * sizeof(float));
+    L.boxes2d = off; off += up256(total * 6 * sizeof(float));
     L.scores = off; off += up256(total * sizeof(float));
     L.offs = off; off += up256(((size_t)images + 1) * sizeof(int));
     L.keep = off; off += up256((size_t)images * (max_inst > 0 ? max_inst : 1) * sizeof(int));
@@ -111,14 +122,18 @@ size_t refine_detections_workspace_bytes(int images, int rois, int max_inst) { r
 
 int launch_refine_detections(const float *rois, const float *probs, const float *deltas, int images, int rois_per_image,
                              int num_classes, const float image_shape[3], const float std_dev[6], float min_conf,
-                             float nms_thr, int max_inst, float *detections, int *det_count, void *ws, size_t ws_bytes,
-                             cudaStream_t stream)
+                             float nms_thr, int nms_mode, int max_inst, float *detections, int *det_count, void *ws,
+                             size_t ws_bytes, cudaStream_t stream)
 {
     const RefineLayout L = refine_layout(images, rois_per_image, max_inst);
     if (ws == nullptr || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return ROI3D_EWORKSPACE;
     char *base = static_cast<char *>(ws);
     float *boxes_px = reinterpret_cast<float *>(base + L.boxes);
     float *scores = reinterpret_cast<float *>(base + L.scores);
+    const bool ref2d = nms_mode == ROI3D_NMS_REFERENCE_2D;
+    float *boxes_nms = ref2d ? reinterpret_cast<float *>(base + L.boxes2d) : nullptr;
+    // tf.image.non_max_suppression suppresses on iou > thr: the same compare as iou >= (thr + 1 ulp)
+    const float thr_eff = ref2d ? nextafterf(nms_thr, INFINITY) : nms_thr;
     int *offs = reinterpret_cast<int *>(base + L.offs);
     int *keep = reinterpret_cast<int *>(base + L.keep);
     int *count = reinterpret_cast<int *>(base + L.count);
@@ -131,9 +146,9 @@ int launch_refine_detections(const float *rois, const float *probs, const float 
     ROI3D_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)images, stream));
     if (total > 0) {
         ROI3D_CUDA_TRY(launch_dependent(refine_decode_kernel, dim3((max(total, images + 1) + 255) / 256), dim3(256), 0, stream, true, rois, probs,
-                                        deltas, total, rois_per_image, images, num_classes, P, boxes_px, scores, offs));
+                                        deltas, total, rois_per_image, images, num_classes, P, boxes_px, boxes_nms, scores, offs));
         ROI3D_LAUNCH_CHECK();
-        const int rc = launch_nms3d(boxes_px, scores, offs, images, rois_per_image, max_inst, nms_thr, keep, count,
+        const int rc = launch_nms3d(ref2d ? boxes_nms : boxes_px, scores, offs, images, rois_per_image, max_inst, thr_eff, keep, count,
                                     base + L.nms, ws_bytes - L.nms, stream);
         if (rc != ROI3D_OK) return rc;
     }

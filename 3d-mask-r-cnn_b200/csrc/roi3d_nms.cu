@@ -506,13 +506,17 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
         __syncthreads();
     }
     const bool self_suppresses = (0.0f >= thr);                // thr == 0: even a zero-volume box suppresses itself
+    // rows kept so far, carried in a register by every thread: s_nsel is written by warp 0 inside an iteration and
+    // may only be read between the barrier that follows the chain and the next barrier (never at the top of the loop,
+    // where a late warp could already see warp 0's new value)
+    int k_cur = k_start;
 
     for (int s = sb_begin; s < s_stop; ++s) {
         const int cur = s & 1, nxt = cur ^ 1;
         unsigned *blk = s_blk + cur * (SC_SB * SC_P);
         const float *bvol = s_vol + cur * SC_SB;
         const int *bsidx = s_sidx + cur * SC_SB;
-        const int k_before = s_nsel;                           // rows kept before this super-chunk: krows[0 .. k_before)
+        const int k_before = k_cur;                            // rows kept before this super-chunk: krows[0 .. k_before)
         if (warp != 0) {
             // background: stage the diagonal block of the next super-chunk and OR the rows kept so far into ITS
             // removed words -- suppression is propagated lazily, one super-chunk ahead, never to columns the scan
@@ -599,9 +603,10 @@ nms_scan_kernel(const unsigned *__restrict__ mask, int pitch_words, const SBox *
             }
         }
         __syncthreads();                                       // also publishes warp 0's krows[] stores to the CTA
+        k_cur = s_nsel;
         if (s_done || s + 1 >= s_stop) break;
         // boundary: the rows kept in THIS super-chunk complete the next super-chunk's removed words
-        sc_or_rows(s_rem[nxt], mask, pitch_words, krows, k_before, s_nsel, (s + 1) * SC_W, nwords, threadIdx.x, SC_THREADS);
+        sc_or_rows(s_rem[nxt], mask, pitch_words, krows, k_before, k_cur, (s + 1) * SC_W, nwords, threadIdx.x, SC_THREADS);
         if (threadIdx.x < SC_W) s_rem[cur][threadIdx.x] = 0u;  // becomes the accumulator of super-chunk s + 2
         __syncthreads();
     }
@@ -715,32 +720,41 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
     const int nsb = (n + SC_SB - 1) / SC_SB;
     int head_sb = (int)(((long long)max_out + max_out / 4 + 256 + SC_SB - 1) / SC_SB);
     if (option_value(OPT_NMS_VARIANT) == 1 || head_sb >= nsb) head_sb = nsb;
-    const int T = min(head_sb * SC_SB, n);
-    {
-        const int words = (T + 31) / 32;
-        const int hrows = (head_sb < nsb) ? 32 : MK_ROWS;      // a small head triangle needs more, smaller CTAs
-        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (T + hrows - 1) / hrows, S);
-        const ScanState *no_state = nullptr;
-        if (hrows == 32)
-            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<32>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
-                                            L.pitch_words, thr, 0, T, no_state, mask));
-        else
-            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
-                                            L.pitch_words, thr, 0, T, no_state, mask));
-        ROI3D_LAUNCH_CHECK();
-        ROI3D_CUDA_TRY(launch_dependent(nms_scan_kernel, dim3(S), dim3(SC_THREADS), smem, stream, pdl, (const unsigned *)mask, L.pitch_words,
-                                        (const SBox *)sboxes, (const int *)sidx, (const int *)nvalid, n, max_out, thr, 0, head_sb, state,
-                                        krows, keep_idx, keep_count));
-        ROI3D_LAUNCH_CHECK();
+    // Phase boundaries in super-chunks.  Up to 8191 boxes: head + tail.  From 8192 boxes the tail -- the bulk of the
+    // n^2 / 2 pairs -- is cut into windows that double in size (at most 4 phases): when the proposals are dense and the
+    // scan has to go a few times deeper than max_out (what a trained RPN produces), only the windows it actually
+    // reaches are computed (20 000 dense boxes: 0.376 -> see profiles/r2_nms_ncu_summary.txt); a window whose
+    // predecessor finished the job costs two kernels that exit at once (~2 us each under PDL).
+    int bounds[5] = {0, head_sb, nsb, nsb, nsb};
+    int nphase = (head_sb < nsb) ? 2 : 1;
+    if (head_sb < nsb && n >= 8192 && option_value(OPT_NMS_VARIANT) != 2) {
+        nphase = 1;
+        int b = head_sb;
+        while (b < nsb && nphase < 4) {
+            const int nb2 = (nphase == 3) ? nsb : min(nsb, 2 * b);
+            bounds[nphase + 1] = nb2;
+            b = nb2;
+            ++nphase;
+        }
+        for (int q = nphase + 1; q < 5; ++q) bounds[q] = nsb;
     }
-    if (head_sb < nsb) {
-        const int wb = T / 32, words = (n + 31) / 32 - wb;
-        dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (n + MK_ROWS - 1) / MK_ROWS, S);
-        ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
-                                        L.pitch_words, thr, wb, n, (const ScanState *)state, mask));
+    for (int ph = 0; ph < nphase; ++ph) {
+        const int sb0 = bounds[ph], sb1 = bounds[ph + 1];
+        const int c0 = min(sb0 * SC_SB, n), c1 = min(sb1 * SC_SB, n);      // columns [c0, c1) for rows [0, c1)
+        const int wb = c0 / 32, words = (c1 + 31) / 32 - wb;
+        const ScanState *st = (ph == 0) ? nullptr : state;
+        if (ph == 0 && nphase > 1) {                           // a small head triangle needs more, smaller CTAs
+            dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (c1 + 31) / 32, S);
+            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<32>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
+                                            L.pitch_words, thr, wb, c1, st, mask));
+        } else {
+            dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (c1 + MK_ROWS - 1) / MK_ROWS, S);
+            ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
+                                            L.pitch_words, thr, wb, c1, st, mask));
+        }
         ROI3D_LAUNCH_CHECK();
         ROI3D_CUDA_TRY(launch_dependent(nms_scan_kernel, dim3(S), dim3(SC_THREADS), smem, stream, pdl, (const unsigned *)mask, L.pitch_words,
-                                        (const SBox *)sboxes, (const int *)sidx, (const int *)nvalid, n, max_out, thr, head_sb, nsb, state,
+                                        (const SBox *)sboxes, (const int *)sidx, (const int *)nvalid, n, max_out, thr, sb0, sb1, state,
                                         krows, keep_idx, keep_count));
         ROI3D_LAUNCH_CHECK();
     }

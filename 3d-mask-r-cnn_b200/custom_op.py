@@ -585,15 +585,22 @@ def proposal_layer(scores, deltas, anchors, std_dev, image_depth, pre_nms_limit,
 # ---------------------------------------------------------------------------------------
 # DetectionLayer, mask targets and the target files' payloads
 # ---------------------------------------------------------------------------------------
+NMS_MODES = {"reference_2d": 0, "3d": 1}
+
+
 def refine_detections(rois, probs, deltas, image_shape, detection_min_confidence, detection_nms_threshold,
-                      bbox_std_dev=None, detection_max_instances=None, return_counts=False):
+                      bbox_std_dev=None, detection_max_instances=None, return_counts=False, nms_mode="reference_2d"):
     """``refine_detections_graph`` (core/models.py:1415-1524) / ``DetectionLayer.call`` (:1552-1575) on the device.
 
     ``rois [R,6]`` / ``probs [R,K]`` / ``deltas [R,K,6]`` for one image, or with a leading batch axis for the whole
     layer (one set of launches, no ``batch_slice`` loop, no host sync).  ``image_shape`` = (H, W, D) in pixels.
     Returns ``detections [max_instances, 8]`` (or ``[B, max_instances, 8]``) =
-    ``(y1,x1,z1,y2,x2,z2,class_id,score)`` normalised, zero padded.  The NMS is the 3-D op (row f3), where the fork
-    calls the 2-D ``tf.image.non_max_suppression`` on (y, x)."""
+    ``(y1,x1,z1,y2,x2,z2,class_id,score)`` normalised, zero padded.
+
+    ``nms_mode="reference_2d"`` (default) is the graph's own NMS: ``tf.image.non_max_suppression`` on the (y, x)
+    projection, suppressing on IoU > threshold (:1496-1501).  ``nms_mode="3d"`` runs the 3-D op instead (IoU over the
+    volume, >= threshold): the upstream design ``utils.non_max_suppression_3d_graph`` exists for; opt-in."""
+    _require(nms_mode in NMS_MODES, "nms_mode must be 'reference_2d' or '3d'")
     dev = _device()
     r, p, d = _Arg(rois, torch.float32, dev), _Arg(probs, torch.float32, dev), _Arg(deltas, torch.float32, dev)
     single = r.dev.dim() == 2
@@ -614,7 +621,7 @@ def refine_detections(rois, probs, deltas, image_shape, detection_min_confidence
         ws = torch.empty(lib.roi3d_refine_detections_workspace_bytes(B, R, M), dtype=torch.uint8, device=dev)
         shp = (ctypes.c_float * 3)(*[float(v) for v in list(image_shape)[:3]])
         _lib.check(lib.roi3d_refine_detections(_ptr(r.dev), _ptr(p.dev), _ptr(d.dev), B, R, K, shp, (ctypes.c_float * 6)(*std),
-                                               float(detection_min_confidence), thr, M, _ptr(det), _ptr(cnt), _ptr(ws),
+                                               float(detection_min_confidence), thr, NMS_MODES[nms_mode], M, _ptr(det), _ptr(cnt), _ptr(ws),
                                                ws.numel(), _stream_ptr()))
     out = det[0] if single else det
     host = r.host or p.host or d.host

@@ -54,9 +54,64 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------
+WORKLOAD_NAME = "cfg2"
+
+
+def run_cfg4(torch, rb, lib, dev, world, peak, ptr, stream, barrier):
+    """BASELINE configs[3] on this rank: one 128^3 image, 1000 ROIs x 14^3 x 256 ch, CropAndResize3D forward + grad-image on
+    the level that receives the ROIs (P2), C-ABI calls replayed from a CUDA graph; whole-job ROIs/s over all ranks."""
+    import ctypes
+    vp = ctypes.c_void_p
+    crop, R = (14, 14, 14), 1000
+    routed = roi3d_synth.pyramid_rois(R, 1, VOLUME, seed=2002)
+    shape = roi3d_synth.level_shape(VOLUME, 2, batch=1)
+    boxes, bidx, _ = routed[2]
+    n = len(boxes)
+    image = torch.from_numpy(roi3d_synth.feature_map(VOLUME, 2, batch=1)).to(dev)
+    tb, ti = torch.from_numpy(boxes).to(dev), torch.from_numpy(bidx).to(dev)
+    torch.manual_seed(44)
+    grads = torch.randn((n,) + crop + (shape[4],), device=dev)
+    crops = torch.empty_like(grads)
+    gimg = torch.empty(shape, device=dev)
+    B, H, W, D, C = shape
+    fb = roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=False)
+    bb = roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=True)
+
+    def fwd():
+        rb._lib.check(lib.roi3d_car3d_fwd(ptr(image), B, H, W, D, C, ptr(tb), ptr(ti), n, 14, 14, 14, 0, 0.0, ptr(crops), stream()))
+
+    def bwd():
+        rb._lib.check(lib.roi3d_car3d_grad_image(ptr(grads), ptr(tb), ptr(ti), n, 14, 14, 14, B, H, W, D, C, 0, ptr(gimg), stream()))
+
+    def ev_time(fn, reps):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return rb.sharding.max_over_ranks(a.elapsed_time(b)) / reps
+    t_f, t_b = ev_time(fwd, 10), ev_time(bwd, 10)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fwd()
+        bwd()
+    t_s = ev_time(gr.replay, 10)
+    del gr, grads, crops, gimg, image
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4: one 128^3 image per GPU, %d ROIs (all on P2) x 14^3 x 256 ch, fwd + grad-image" % n,
+            "ms_per_step": round(t_s, 4), "value": round(world * n / (t_s * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "fwd_ms": round(t_f, 4), "fwd_frac": round(fb / (t_f * 1e-3) / 1e9 / peak, 4),
+            "bwd_ms": round(t_b, 4), "bwd_frac": round(bb / (t_b * 1e-3) / 1e9 / peak, 4)}
+
+
 def set_workload(name):
     """cfg2 (default, BASELINE configs[1]) or cfg4 (configs[3]: mask-head stress, 1000 ROIs x 14^3 x 256 ch, one image per GPU)."""
-    global BATCH, ROIS_PER_IMAGE, CROPS, WORKLOAD
+    global BATCH, ROIS_PER_IMAGE, CROPS, WORKLOAD, WORKLOAD_NAME
+    WORKLOAD_NAME = name
     if name == "cfg4":
         BATCH, ROIS_PER_IMAGE, CROPS = 1, 1000, ((14, 14, 14),)
         WORKLOAD = ("cfg4: mask-head stress, one 128^3 image per GPU, 1000 ROIs x 14^3 x 256 ch over P2-P5, "
@@ -253,10 +308,17 @@ def run_ours(args):
     # ---- per-op timing (CUDA events on the launching stream) -> roofline of the dominant kernel ----
     peak, peak_src = load_peaks()
     per_op = []
-    reps = max(args.steps, 5)
+    reps = max(args.steps, 30)
+
+    def pct(v, q):
+        v = sorted(v)
+        return v[min(len(v) - 1, int(q * len(v)))]
+
     for kind, fn in (("fwd", fwd), ("bwd", bwd)):
         for op in ops:
             evs = []
+            for _ in range(3):
+                fn(op)
             for _ in range(reps):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -264,21 +326,24 @@ def run_ours(args):
                 b.record()
                 evs.append((a, b))
             torch.cuda.synchronize()
-            ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+            t = [a.elapsed_time(b) for a, b in evs]
+            ms = statistics.mean(t)
             nbytes = op[kind + "_bytes"]
             per_op.append({"op": "car3d_" + ("fwd" if kind == "fwd" else "grad_image"), "level": op["level"],
-                           "crop": op["crop"][0], "n": op["n"], "ms": round(ms, 4), "alg_bytes": nbytes,
+                           "crop": op["crop"][0], "n": op["n"], "ms": round(ms, 4), "ms_p10": round(pct(t, 0.1), 4),
+                           "ms_p50": round(pct(t, 0.5), 4), "ms_p90": round(pct(t, 0.9), 4), "reps": reps, "alg_bytes": nbytes,
                            "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else None})
     dom = max(per_op, key=lambda r: r["ms"])
     dom_name = "%s P%d crop %d^3 n=%d" % (dom["op"], dom["level"], dom["crop"], dom["n"])
     try:                                   # DRAM bytes per launch measured once with `ncu --set full` (profiles/README.md)
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic_r2.json")) as f:
             traffic = json.load(f).get(dom_name) if rank == 0 and seed_is_default else None
     except Exception:  # noqa: BLE001
         traffic = None
     roofline = {"bound": "hbm", "kernel": dom_name,
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
+                "ms": dom["ms"], "ms_p10": dom["ms_p10"], "ms_p50": dom["ms_p50"], "ms_p90": dom["ms_p90"], "reps": reps,
                 "note": "achieved = algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration of the C-ABI call"
                         + (" (zero-fill memset + scatter kernel)" if dom["op"].endswith("grad_image") else "")}
     sum_bytes = sum(r["alg_bytes"] for r in per_op)
@@ -307,17 +372,32 @@ def run_ours(args):
 
     for _ in range(3):
         fused_step()
+    torch.cuda.synchronize()
+    rb.reset_kernel_launches()
+    run_fused = fused_step
+    if not args.no_graph:                               # same launch mode as the per-op step it is compared with
+        fgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fgraph):
+            fused_step()
+        run_fused = fgraph.replay
+    fused_launches = rb.kernel_launches()
+    for _ in range(5):
+        run_fused()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        fused_step()
+        run_fused()
     f1.record()
     barrier()
     fused_ms = rb.sharding.max_over_ranks(f0.elapsed_time(f1)) / args.steps
     fused = {"ms_per_step": round(fused_ms, 4), "value": round(world * total_rois / (fused_ms * 1e-3), 1), "unit": UNIT,
-             "launches_per_step": 4, "note": "roi3d_pyramid_roi_align_fwd/grad: routing + 4 levels + order restore in one "
-             "launch per pool shape (7^3 uses the plane kernel here, the per-op path picks the direct kernel)"}
+             "launches_per_step": int(fused_launches) if not args.no_graph else None,
+             "vs_per_op_step": round(fused_ms / ms_step, 4),
+             "note": "roi3d_pyramid_roi_align_fwd/grad: routing + 4 levels + order restore in one launch per pool shape, one "
+                     "zero-fill kernel for the four grad maps; same launch mode (CUDA graph replay) as the per-op step"}
+    if not args.no_graph:
+        del fgraph
     # float16 output (the target files' payload) written by the crop kernel vs float32 crop + separate conversion
     f16 = {}
     for c in CROPS:
@@ -343,36 +423,46 @@ def run_ours(args):
     fused["f16_output"] = f16
     del pooled, pgrads, gms
 
-    # ---- NMS3D @6k boxes (cfg1: 6000 -> 1000 @0.7), device resident and host-buffer end to end ----
-    nb, ns = roi3d_synth.nms_boxes(6000, VOLUME)
+    # ---- NMS3D: cfg1 (6000 -> 1000 @0.7), cfg3 (20000 -> 2000 @0.7), and the dense-cluster regime a trained RPN produces ----
+    def time_nms(n, max_out, thr, vol, reps=50, **kw):
+        bx, sc = roi3d_synth.nms_boxes(n, vol, **kw)
+        d_b, d_s = torch.from_numpy(bx).to(dev), torch.from_numpy(sc).to(dev)
+        nws = lib.roi3d_nms3d_workspace_bytes(n)
+        wsp = torch.empty(nws, dtype=torch.uint8, device=dev)
+        kp = torch.empty(max_out, dtype=torch.int32, device=dev)
+        ct = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def call():
+            rb._lib.check(lib.roi3d_nms3d(ptr(d_b), ptr(d_s), n, max_out, thr, ptr(kp), ptr(ct), ptr(wsp), nws, stream()))
+
+        def loop(fn):
+            out = []
+            for it in range(reps + 10):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                if it >= 10:
+                    out.append(a.elapsed_time(b))
+            return sorted(out)
+        eager = loop(call)
+        gr = torch.cuda.CUDAGraph()                     # the call is stream-ordered and allocation-free: capturable as is
+        with torch.cuda.graph(gr):
+            call()
+        replay = loop(gr.replay)
+        del gr
+        med = eager[len(eager) // 2]
+        return {"boxes": n, "max_out": max_out, "iou_threshold": thr, "kept": int(ct.item()), "ms": round(med, 4),
+                "ms_p10": round(eager[len(eager) // 10], 4), "ms_p90": round(eager[len(eager) * 9 // 10], 4),
+                "ms_graph_replay": round(replay[len(replay) // 2], 4), "boxes_per_s": round(n / (med * 1e-3)),
+                "pairs_per_s": round(n * (n - 1) / 2 / (med * 1e-3))}, (bx, sc, kp, ct)
+
+    nms, (nb, ns, keep, cnt) = time_nms(6000, 1000, 0.7, VOLUME)
+    nms20, _ = time_nms(20000, 2000, 0.7, (256, 256, 256), reps=30)
+    nms_dense, _ = time_nms(6000, 1000, 0.7, VOLUME, reps=30, cluster=64, jitter=0.05)
+    nms20_dense, _ = time_nms(20000, 2000, 0.7, (256, 256, 256), reps=20, cluster=64, jitter=0.05)
     d_nb, d_ns = torch.from_numpy(nb).to(dev), torch.from_numpy(ns).to(dev)
-    wsb = lib.roi3d_nms3d_workspace_bytes(6000)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    keep = torch.empty(1000, dtype=torch.int32, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-    nms_ms = []
-    for it in range(60):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        rb._lib.check(lib.roi3d_nms3d(ptr(d_nb), ptr(d_ns), 6000, 1000, 0.7, ptr(keep), ptr(cnt), ptr(ws), wsb, stream()))
-        b.record()
-        torch.cuda.synchronize()
-        if it >= 10:
-            nms_ms.append(a.elapsed_time(b))
-    # the same call replayed from a CUDA graph (stream-ordered, allocation-free: capturable as is)
-    nms_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(nms_graph):
-        rb._lib.check(lib.roi3d_nms3d(ptr(d_nb), ptr(d_ns), 6000, 1000, 0.7, ptr(keep), ptr(cnt), ptr(ws), wsb, stream()))
-    nms_g_ms = []
-    for it in range(60):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        nms_graph.replay()
-        b.record()
-        torch.cuda.synchronize()
-        if it >= 10:
-            nms_g_ms.append(a.elapsed_time(b))
-    del nms_graph
     for _ in range(3):                                  # warm the workspace / pinned-buffer caches
         rb.non_max_suppression_3d(nb, ns, 1000, 0.7)
     torch.cuda.synchronize()
@@ -399,12 +489,9 @@ def run_ours(args):
         if it >= 5:
             b_ms.append(a.elapsed_time(b))
     del ws8
-    nms = {"boxes": 6000, "max_out": 1000, "iou_threshold": 0.7, "kept": int(cnt.item()),
-           "batched_8x6000_ms": round(statistics.median(b_ms), 4),
-           "ms": round(statistics.median(nms_ms), 4), "ms_graph_replay": round(statistics.median(nms_g_ms), 4), "ms_p10": round(sorted(nms_ms)[len(nms_ms) // 10], 4),
-           "ms_p90": round(sorted(nms_ms)[len(nms_ms) * 9 // 10], 4),
-           "boxes_per_s": round(6000 / (statistics.median(nms_ms) * 1e-3)),
-           "e2e_host_buffers_ms": round(nms_e2e_ms, 4), "e2e_kept": int(len(kept))}
+    nms.update({"batched_8x6000_ms": round(statistics.median(b_ms), 4), "e2e_host_buffers_ms": round(nms_e2e_ms, 4),
+                "e2e_kept": int(len(kept)), "cfg3_20000_to_2000": nms20, "dense_clusters_6000": nms_dense,
+                "dense_clusters_20000": nms20_dense})
 
     # ---- ProposalLayer on the device (cfg1 front half): top-k 6000 of N anchors -> decode -> NMS3D -> pad ----
     n_anchor = 393216                                   # 32*32*128*3 anchors of the finest RPN level at 128^3
@@ -518,6 +605,27 @@ def run_ours(args):
     e2e_s = rb.sharding.max_over_ranks(e2e_s)
     e2e_value = world * total_rois * e2e_steps / e2e_s
 
+    # ---- BASELINE configs[3] (cfg4: mask-head stress, one image per GPU, 1000 ROIs x 14^3 x 256 ch) on every rank ----
+    cfg4 = None
+    if WORKLOAD_NAME == "cfg2" and not args.no_cfg4:
+        try:
+            cfg4 = run_cfg4(torch, rb, lib, dev, world, peak, ptr, stream, barrier)
+        except torch.cuda.OutOfMemoryError:             # bounded: never take the box down for an extra key
+            cfg4 = {"skipped": "out of memory"}
+    # the other half of BASELINE's metric and the rows the driver record keeps only inside `roofline`
+    roofline["secondary"] = {
+        "nms3d_ms_6k": nms["ms"], "nms3d_ms_6k_graph_replay": nms["ms_graph_replay"], "nms3d_boxes_per_s_6k": nms["boxes_per_s"],
+        "nms3d_pairs_per_s_6k": nms["pairs_per_s"], "nms3d_kept_6k": nms["kept"],
+        "nms3d_ms_20k": nms20["ms"], "nms3d_boxes_per_s_20k": nms20["boxes_per_s"], "nms3d_pairs_per_s_20k": nms20["pairs_per_s"],
+        "nms3d_ms_6k_dense_clusters": nms_dense["ms"], "nms3d_ms_20k_dense_clusters": nms20_dense["ms"],
+        "nms3d_batched_8x6000_ms": nms["batched_8x6000_ms"],
+        "nms3d_bound": "SM fp32 ALU / L2 (IoU bitmask) + latency (greedy scan); ncu counters: profiles/r2_nms_ncu_summary.txt",
+        "pyramid_fused_ms_per_step": fused["ms_per_step"], "per_op_ms_per_step": round(ms_step, 4),
+        "cfg4": cfg4,
+        "per_op": [{k: r[k] for k in ("op", "level", "crop", "n", "ms", "ms_p10", "ms_p90", "gbs")} |
+                   {"frac": round(r["gbs"] / peak, 4) if r["gbs"] else None} for r in per_op if r["n"]],
+    }
+
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
@@ -544,17 +652,17 @@ def run_ours(args):
         "ops": per_op,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, ref = _cpu_engines()
-        nthr = host_threads()
-        if ref is not None:
-            full = BATCH * ROIS_PER_IMAGE
-            line["cpu_baseline"] = cpu_baseline(ops, "reference", min(nthr, 16), full, repeats=5)
-            line["cpu_baseline_reference_1thread"] = cpu_baseline(ops, "reference", 1, full, repeats=2)
-            line["cpu_baseline_port_allcores"] = cpu_baseline(ops, "port", nthr, full, repeats=5)
-        else:
-            full = BATCH * ROIS_PER_IMAGE
-            line["cpu_baseline"] = cpu_baseline(ops, "port", nthr, full, repeats=10)
-            line["cpu_baseline_port_1thread"] = cpu_baseline(ops, "port", 1, full, repeats=2)
+        # The CPU baseline (oracle port / the reference's own binaries) runs in a CHILD process: this process -- the
+        # product arm -- never maps anything under oracle/.
+        del ops, images
+        torch.cuda.empty_cache()
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-child", "all", "--workload", WORKLOAD_NAME],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        try:
+            line.update(json.loads(res.stdout.strip().splitlines()[-1]))
+        except Exception:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": "CPU baseline child failed: " + (res.stderr or res.stdout)[-300:]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -637,6 +745,26 @@ def cpu_baseline(ops, kind, threads, sample_rois, repeats=1):
             "ms_per_step": round(t_step * 1e3, 1)}
 
 
+def run_cpu_baseline_child():
+    """Child process of the GPU arm: times the reference's CPU implementation of the step and prints one JSON object."""
+    _, ref = _cpu_engines()
+    if ref is not None:
+        from oracle import refrun
+        refrun.harden_process()
+    ops = make_workload(seed=2002)
+    nthr = host_threads()
+    full = BATCH * ROIS_PER_IMAGE
+    out = {}
+    if ref is not None:
+        out["cpu_baseline"] = cpu_baseline(ops, "reference", min(nthr, 16), full, repeats=5)
+        out["cpu_baseline_reference_1thread"] = cpu_baseline(ops, "reference", 1, full, repeats=2)
+        out["cpu_baseline_port_allcores"] = cpu_baseline(ops, "port", nthr, full, repeats=5)
+    else:
+        out["cpu_baseline"] = cpu_baseline(ops, "port", nthr, full, repeats=10)
+        out["cpu_baseline_port_1thread"] = cpu_baseline(ops, "port", 1, full, repeats=2)
+    print(json.dumps(out))
+
+
 def host_threads():
     """Host cores available to this process (torchrun exports OMP_NUM_THREADS=1, which must not shrink the baseline)."""
     try:
@@ -653,6 +781,9 @@ def run_reference(args):
         return
     oracle, ref = _cpu_engines()
     kind = "reference" if ref is not None else "port"
+    if ref is not None:                                 # this process only ever runs the reference: lock it down
+        from oracle import refrun
+        refrun.harden_process()
     ops = make_workload(seed=2002)
     threads = min(host_threads(), 16) if kind == "reference" else host_threads()
     total = BATCH * ROIS_PER_IMAGE
@@ -692,9 +823,13 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager C-ABI calls instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the extra BASELINE configs[3] measurement")
+    ap.add_argument("--cpu-baseline-child", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     set_workload(args.workload)
-    if args.impl == "reference":
+    if args.cpu_baseline_child:
+        run_cpu_baseline_child()
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -19,8 +19,10 @@
  *
  * Ownership / threading: every pointer is a DEVICE pointer on the current CUDA
  * device unless stated otherwise and is owned by the caller (TF allocator,
- * torch, cudaMalloc ...).  The library allocates nothing, keeps no pointer and
- * has no mutable global state: all calls are re-entrant.  All work is enqueued
+ * torch, cudaMalloc ...).  The library allocates nothing and keeps no pointer; all calls are re-entrant.  Its only
+ * state is (i) per calling thread: the last CUDA error, the launch counter and the tuning options of
+ * roi3d_set_option, (ii) process-wide, write-once caches of device facts (SM count, shared-memory opt-in already
+ * granted to a kernel).  No call can change what another thread's call computes.  All work is enqueued
  * on `stream` (a cudaStream_t passed as void*); no call synchronizes the device
  * or the stream.  Return value: ROI3D_OK or a negative ROI3D_E* code; nothing
  * is thrown and nothing aborts.
@@ -106,8 +108,10 @@ ROI3D_API int roi3d_nms3d_batched(const float *boxes, const float *scores, const
  * replaces: REGISTER_OP("CropAndResize3D") + CropAndResize3DOp::Compute (CAR.so@0x4370);
  *           Python: core/custom_op/custom_op.py:22, called from core/models.py:663-664
  *           (PyramidROIAlign) and core/models.py:992-994 (mask targets).
- * box_index[i] selects the batch item of box i and must lie in [0,B) (the
- * reference does not check it either).  n == 0 is valid (nothing is launched).
+ * box_index[i] selects the batch item of box i.  The reference does not check it (an index outside [0,B) reads
+ * out of bounds there); here such a box reads nothing: its crop is filled with extrapolation_value, it scatters
+ * nothing in CropAndResize3DGradImage and its CropAndResize3DGradBoxes row is zero.  n == 0 is valid (nothing is
+ * launched).
  * ------------------------------------------------------------------------- */
 ROI3D_API int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
                               const float *boxes, const int *box_index, int n,
@@ -197,9 +201,14 @@ ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, 
 /* ---------------------------------------------------------------------------
  * DetectionLayer on the device
  * replaces: refine_detections_graph + the utils.batch_slice loop of DetectionLayer.call, core/models.py:1415-1575, for
- *           the whole batch in one set of launches, with the 3-D op as the NMS (the fork calls the 2-D
- *           tf.image.non_max_suppression on y/x, :1496-1501; utils.non_max_suppression_3d_graph, core/utils.py:467-503,
- *           is the wrapper the 3-D op was meant to be reached through).
+ *           the whole batch in one set of launches.
+ * nms_mode  ROI3D_NMS_REFERENCE_2D: the NMS this fork's graph performs -- tf.image.non_max_suppression on the (y, x)
+ *           projection of the refined boxes, suppressing on IoU > threshold (core/models.py:1496-1501).  It runs on the
+ *           3-D kernels with every box given the depth interval [0, 1], which makes IoU3D == IoU2D bit for bit, and the
+ *           threshold moved up by one ulp (iou > t <=> iou >= nextafter(t)).  This is the drop-in behaviour.
+ *           ROI3D_NMS_3D: the 3-D op (IoU over the volume, suppressing on IoU >= threshold): the upstream design that
+ *           utils.non_max_suppression_3d_graph (core/utils.py:467-503) was written for and BASELINE cfg3 names; opt-in,
+ *           its detections differ from the fork's whenever boxes overlap in y/x but not in z.
  * rois [B,R,6] normalised, probs [B,R,num_classes], deltas [B,R,num_classes,6] (device, float32).  As in this fork
  * the class is always 1 (fg_probs = probs[:,1], :1441).  Per ROI: score >= min_confidence, deltas * std_dev,
  * apply_box_deltas_3d_graph in pixels (core/utils.py:412-464), clip to [0,H]x[0,W]x[0,D], sizes >= (1,1,0.5) px; NMS
@@ -209,10 +218,11 @@ ROI3D_API int roi3d_decode_proposals(const float *anchors, const float *deltas, 
  * image_shape / std_dev are host arrays.  No host synchronisation.  workspace:
  * roi3d_refine_detections_workspace_bytes(B, R, max_instances), 256-byte aligned.
  * ------------------------------------------------------------------------- */
+enum { ROI3D_NMS_REFERENCE_2D = 0, ROI3D_NMS_3D = 1 };
 ROI3D_API size_t roi3d_refine_detections_workspace_bytes(int images, int rois_per_image, int max_instances);
 ROI3D_API int roi3d_refine_detections(const float *rois, const float *probs, const float *deltas, int images,
                                       int rois_per_image, int num_classes, const float image_shape[3],
-                                      const float std_dev[6], float min_confidence, float nms_threshold,
+                                      const float std_dev[6], float min_confidence, float nms_threshold, int nms_mode,
                                       int max_instances, float *detections, int *det_count,
                                       void *workspace, size_t workspace_bytes, roi3d_stream_t stream);
 

@@ -267,9 +267,44 @@ def refine_decode(rois, probs, deltas, image_shape, min_confidence, bbox_std_dev
     return out.astype(np.float32), score, ok
 
 
+def non_max_suppression_2d_tf(boxes4, scores, max_output_size, iou_threshold):
+    """tf.image.non_max_suppression (NonMaxSuppressionV3, TF r2.2 core/kernels/non_max_suppression_op.cc) restated from
+    the published algorithm -- TensorFlow is absent here, so this restatement is UNPINNED by execution: candidates by
+    descending score (ties -> lower index), a candidate is dropped when its IoU with a selected box is > threshold
+    (strict), IoU in float32 as area_i = (ymax - ymin) * (xmax - xmin), inter / (area_i + area_j - inter), 0 for an
+    empty box.  Called like the reference does (core/models.py:1496-1501), i.e. with (x1, y1, x2, y2) columns."""
+    b = np.ascontiguousarray(boxes4, np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(scores, np.float32).reshape(-1)
+    order = np.lexsort((np.arange(len(s)), -s.astype(np.float64)))
+    order = [i for i in order if s[i] > -np.finfo(np.float32).max]
+    f = np.float32
+    lo0, hi0 = np.minimum(b[:, 0], b[:, 2]), np.maximum(b[:, 0], b[:, 2])
+    lo1, hi1 = np.minimum(b[:, 1], b[:, 3]), np.maximum(b[:, 1], b[:, 3])
+    area = ((hi0 - lo0).astype(f) * (hi1 - lo1).astype(f)).astype(f)
+    thr = f(iou_threshold)
+    sel = []
+    for i in order:
+        if len(sel) >= int(max_output_size):
+            break
+        if sel:
+            j = np.asarray(sel)
+            d0 = np.maximum((np.minimum(hi0[i], hi0[j]) - np.maximum(lo0[i], lo0[j])).astype(f), f(0))
+            d1 = np.maximum((np.minimum(hi1[i], hi1[j]) - np.maximum(lo1[i], lo1[j])).astype(f), f(0))
+            inter = (d0 * d1).astype(f)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                iou = (inter / ((area[i] + area[j]).astype(f) - inter).astype(f)).astype(f)
+            iou = np.where((area[i] <= 0) | (area[j] <= 0), f(0), iou)
+            if np.any(iou > thr):
+                continue
+        sel.append(int(i))
+    return np.asarray(sel, np.int32)
+
+
 def refine_detections(rois, probs, deltas, image_shape, min_confidence, nms_threshold,
-                      bbox_std_dev=(0.1, 0.1, 0.1, 0.2, 0.2, 0.2), max_instances=200, boxes_px=None):
-    """refine_detections_graph (core/models.py:1415-1524) for one image with the 3-D op as its NMS (row f3).
+                      bbox_std_dev=(0.1, 0.1, 0.1, 0.2, 0.2, 0.2), max_instances=200, boxes_px=None, nms_mode="reference_2d"):
+    """refine_detections_graph (core/models.py:1415-1524) for one image, restated from the graph source (TensorFlow is
+    absent: unpinned by execution).  ``nms_mode="reference_2d"``: the graph's own tf.image.non_max_suppression on the
+    (y, x) projection; ``"3d"``: the 3-D op as the NMS (the upstream design, row f3).
     ``boxes_px`` overrides the decoded pixel boxes (tests pass the device's, whose expf may differ in the last ulp,
     to compare the selection exactly)."""
     px, score, ok = refine_decode(rois, probs, deltas, image_shape, min_confidence, bbox_std_dev)
@@ -279,7 +314,12 @@ def refine_detections(rois, probs, deltas, image_shape, min_confidence, nms_thre
     ix = np.nonzero(ok)[0]
     if len(ix) == 0:
         return det
-    sel = non_max_suppression_3d(px[ix], score[ix], int(max_instances), float(nms_threshold))
+    if nms_mode == "3d":
+        sel = non_max_suppression_3d(px[ix], score[ix], int(max_instances), float(nms_threshold))
+    else:
+        p = px[ix]
+        sel = non_max_suppression_2d_tf(np.stack([p[:, 1], p[:, 0], p[:, 4], p[:, 3]], axis=1), score[ix],
+                                        int(max_instances), float(nms_threshold))
     fb, fs = px[ix][sel], score[ix][sel]
     order = np.argsort(-fs, kind="stable")                                 # tf.nn.top_k: descending, ties -> lower index
     fb, fs = fb[order], fs[order]

@@ -30,6 +30,46 @@ MEMBERS = {
     "nms": "non_max_suppression_3d/python/ops/_non_max_suppression_3d_ops.so",
 }
 RUNNER = os.path.join(REF_DIR, "librefrun.so")
+# Provenance pin: SHA-256 of the four members of the reference wheel.  Anything else in oracle/_ref/ is refused --
+# this package executes those files' machine code in-process, so they must be exactly the reference's own binaries.
+PINNED_SHA256 = {
+    "car": "5e37f9b340e19be8665dea48009474d094c1e2f621ce7cdd997ae2edaec60fc0",
+    "gi": "59aa4c2314a15ecfaab139a6fa4675e7c8488ac07b9590f77b334a1cbfaf52ae",
+    "gb": "3b7b24cee72c711788d41d19540cf2fffd29c296e23b498855393beb821fc24f",
+    "nms": "bc5da3c474b8a9775bae8bed45ba071f898e9a0660e6ba6bfbeed4d2354ae40e",
+}
+
+
+def enabled():
+    """ROI3D_REFRUN=0 switches the reference runner off everywhere (tests skip, bench.py falls back to the C port)."""
+    return os.environ.get("ROI3D_REFRUN", "1").lower() not in ("0", "no", "off", "false")
+
+
+def verify():
+    """Raise unless every library in oracle/_ref/ is byte-identical (SHA-256) to the pinned reference wheel member."""
+    import hashlib
+    for key, path in lib_paths().items():
+        with open(path, "rb") as f:
+            got = hashlib.sha256(f.read()).hexdigest()
+        if got != PINNED_SHA256[key]:
+            raise RuntimeError("refrun: %s does not match the pinned reference binary (sha256 %s); refusing to load it" % (path, got))
+
+
+def harden_process():
+    """For the dedicated child processes that run the reference (bench.py's CPU baseline): no new privileges, no core
+    dumps, no file writes, own network namespace when the kernel allows it.  Best effort, never fatal."""
+    import resource
+    for lim, val in ((resource.RLIMIT_CORE, 0), (resource.RLIMIT_FSIZE, 0)):
+        try:
+            resource.setrlimit(lim, (val, val))
+        except (ValueError, OSError):
+            pass
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        libc.prctl(38, 1, 0, 0, 0)                     # PR_SET_NO_NEW_PRIVS
+        libc.unshare(0x40000000)                       # CLONE_NEWNET: the child has no network at all
+    except Exception:  # noqa: BLE001
+        pass
 _f32p, _i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
 
 
@@ -38,7 +78,7 @@ def lib_paths():
 
 
 def available():
-    return os.path.exists(RUNNER) and all(os.path.exists(p) for p in lib_paths().values())
+    return enabled() and os.path.exists(RUNNER) and all(os.path.exists(p) for p in lib_paths().values())
 
 
 def build(force=False):
@@ -54,6 +94,7 @@ def build(force=False):
     missing = [p for p in paths.values() if not os.path.exists(p)]
     if missing:
         raise RuntimeError("reference libraries unavailable (no wheel at %s and no extraction in %s)" % (WHEEL, REF_DIR))
+    verify()
     src = os.path.join(_HERE, "refrun.cc")
     if force or not os.path.exists(RUNNER) or os.path.getmtime(src) > os.path.getmtime(RUNNER):
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=0",
@@ -141,8 +182,11 @@ _ref = None
 def load():
     """Build if needed, map the reference libraries and return a :class:`Reference`."""
     global _ref
+    if not enabled():
+        raise RuntimeError("refrun disabled (ROI3D_REFRUN=0)")
     if _ref is None:
         build()
+        verify()
         lib = ctypes.CDLL(RUNNER, mode=ctypes.RTLD_GLOBAL)      # its stand-in symbols must be visible to dlsym
         lib.refrun_last_error.restype = ctypes.c_char_p
         lib.refrun_open.argtypes = [ctypes.c_char_p] * 4

@@ -32,15 +32,17 @@ def detection_inputs(seed, B, R, K, vol=(128, 128, 128)):
     (1, 1000, 2, 0.5, 0.3, 100), (2, 2000, 2, 0.7, 0.3, 200), (3, 257, 3, 0.0, 0.5, 400), (1, 1, 2, 0.0, 0.3, 5),
     (2, 64, 2, 0.999999, 0.3, 10),
 ])
-def test_refine_detections_matches_restated_graph(rb, cuda_device, B, R, K, min_conf, thr, max_inst):
+@pytest.mark.parametrize("nms_mode", ["reference_2d", "3d"])
+def test_refine_detections_matches_restated_graph(rb, cuda_device, B, R, K, min_conf, thr, max_inst, nms_mode):
     rois, probs, deltas = detection_inputs(4000 + R, B, R, K)
     shape = (128.0, 128.0, 64.0)
     det, cnt = rb.refine_detections(dev(rois, cuda_device), dev(probs, cuda_device), dev(deltas, cuda_device), shape,
-                                    min_conf, thr, None, max_inst, return_counts=True)
+                                    min_conf, thr, None, max_inst, return_counts=True, nms_mode=nms_mode)
     det, cnt = det.cpu().numpy(), cnt.cpu().numpy()
     assert det.shape == (B, max_inst, 8)
     for b in range(B):
-        ref = oracle.refine_detections(rois[b], probs[b], deltas[b], shape, min_conf, thr, max_instances=max_inst)
+        # the device's own decoded boxes (expf may differ from numpy's exp in the last ulp) -> the selection is compared exactly
+        ref = oracle.refine_detections(rois[b], probs[b], deltas[b], shape, min_conf, thr, max_instances=max_inst, nms_mode=nms_mode)
         k = int((ref[:, 6] > 0).sum())
         assert cnt[b] == k
         assert np.array_equal(det[b, :, 7], ref[:, 7])                     # same ROIs, same order (scores are copied)
@@ -50,8 +52,33 @@ def test_refine_detections_matches_restated_graph(rb, cuda_device, B, R, K, min_
         assert np.all(np.diff(det[b, :k, 7]) <= 0)                         # descending score
     # single-image call == row of the batched call
     one = rb.refine_detections(dev(rois[0], cuda_device), dev(probs[0], cuda_device), dev(deltas[0], cuda_device), shape,
-                               min_conf, thr, None, max_inst).cpu().numpy()
+                               min_conf, thr, None, max_inst, nms_mode=nms_mode).cpu().numpy()
     assert np.array_equal(one, det[0])
+
+
+def test_refine_detections_2d_vs_3d_and_threshold_tie(rb, cuda_device):
+    """Boxes stacked along z overlap fully in (y, x) and not at all in z: the fork's 2-D NMS keeps one, the 3-D op keeps
+    all.  And the compare rules differ exactly at IoU == threshold: tf.image suppresses on >, the 3-D op on >=."""
+    n = 6
+    rois = np.zeros((n, 6), np.float32)
+    for i in range(n):                                       # same (y, x) square, disjoint z slabs
+        rois[i] = [0.25, 0.25, i / 8.0, 0.5, 0.5, (i + 0.9) / 8.0]
+    probs = np.stack([np.full(n, 0.1, np.float32), np.linspace(0.9, 0.6, n).astype(np.float32)], axis=1)
+    deltas = np.zeros((n, 2, 6), np.float32)
+    shape = (128.0, 128.0, 64.0)
+    args = (dev(rois, cuda_device), dev(probs, cuda_device), dev(deltas, cuda_device), shape, 0.5, 0.3, None, 10)
+    d2 = rb.refine_detections(*args, nms_mode="reference_2d").cpu().numpy()
+    d3 = rb.refine_detections(*args, nms_mode="3d").cpu().numpy()
+    assert int((d2[:, 6] > 0).sum()) == 1 and int((d3[:, 6] > 0).sum()) == n
+    for mode, d in (("reference_2d", d2), ("3d", d3)):
+        assert np.array_equal(d[:, 7], oracle.refine_detections(rois, probs, deltas, shape, 0.5, 0.3, max_instances=10, nms_mode=mode)[:, 7])
+    # IoU exactly 0.5: box A = [0,64]x[0,64], box B = [0,64]x[0,32] in pixels (area ratio 1/2, all values exact in fp32)
+    rois = np.array([[0, 0, 0, 0.5, 0.5, 0.5], [0, 0, 0, 0.5, 0.25, 0.5]], np.float32)
+    probs = np.array([[0.1, 0.9], [0.2, 0.8]], np.float32)
+    deltas = np.zeros((2, 2, 6), np.float32)
+    args = (dev(rois, cuda_device), dev(probs, cuda_device), dev(deltas, cuda_device), shape, 0.5, 0.5, None, 4)
+    assert int((rb.refine_detections(*args, nms_mode="reference_2d").cpu().numpy()[:, 6] > 0).sum()) == 2   # 0.5 > 0.5 is false
+    assert int((rb.refine_detections(*args, nms_mode="3d").cpu().numpy()[:, 6] > 0).sum()) == 1             # 0.5 >= 0.5
 
 
 def test_refine_detections_host_buffers_and_errors(rb, cuda_device):

@@ -62,6 +62,20 @@ def test_nms_matches_oracle(rb, cuda_device, n, thr, max_out, presorted):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n,max_out,thr", [(6000, 1000, 0.7), (20000, 2000, 0.7), (20000, 2000, 0.5), (9000, 300, 0.7), (33000, 4000, 0.6)])
+def test_nms_dense_clusters_deep_scan(rb, cuda_device, n, max_out, thr):
+    """Dense proposals (clusters of 64 near-duplicates, what a trained RPN emits): the scan goes several times deeper than
+    max_out, through the windowed tail phases (>= 8192 boxes).  Every schedule must give the oracle's indices."""
+    boxes, scores = roi3d_synth.nms_boxes(n, (256, 256, 256), seed=4100 + n, cluster=64, jitter=0.05)
+    ref = oracle.non_max_suppression_3d(boxes, scores, max_out, thr)
+    try:
+        for variant in (0, 1, 2):                           # windowed tail, single phase, head + one tail
+            rb.custom_op.set_option("nms_variant", variant)
+            assert np.array_equal(run_nms(rb, cuda_device, boxes, scores, max_out, thr), ref), variant
+    finally:
+        rb.custom_op.set_option("nms_variant", 0)
+
+
 def test_nms_golden(rb, cuda_device):
     z = np.load(os.path.join(GOLDEN, "nms.npz"))
     for n in (300, 1000, 64):
@@ -249,6 +263,34 @@ def test_car_empty_and_single(rb, cuda_device):
     gi = rb.crop_and_resize_3d_grad_image(g, e6, ei, (1, 4, 4, 4, 8))
     assert tuple(gi.shape) == (1, 4, 4, 4, 8) and float(gi.abs().sum()) == 0.0     # zero-filled like GI.so@0x3ec5
     assert tuple(rb.crop_and_resize_3d_grad_boxes(g, image, e6, ei).shape) == (0, 6)
+
+
+@pytest.mark.parametrize("case", [CAR_CASES[0], CAR_CASES[1], CAR_CASES[7]])
+def test_car_box_index_out_of_range_is_guarded(rb, cuda_device, case):
+    """The reference reads out of bounds for a box_index outside [0, B) (no check in CAR.so / GI.so / GB.so).  Here
+    such a box reads nothing: crop = extrapolation value, no scatter, zero grad-boxes row; the other boxes are untouched."""
+    B, H, W, D, C, n, crop = case
+    image, boxes, bidx, grads = car_inputs(900 + C, B, H, W, D, C, n, crop, wild=False)
+    bad = np.zeros(n, bool)
+    bad[[1, n // 2, n - 1]] = True
+    bidx_bad = bidx.copy()
+    bidx_bad[bad] = [-1, B, 2 ** 30]
+    good = ~bad
+    t = [dev(x, cuda_device) for x in (image, boxes, bidx_bad, grads)]
+    for fv in (1, 2, 3):
+        rb.custom_op.set_option("car_fwd_variant", fv)
+        out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=7.0).cpu().numpy()
+        assert np.array_equal(out[good], oracle.crop_and_resize_3d(image, boxes[good], bidx[good], crop, "trilinear", 7.0))
+        assert np.all(out[bad] == 7.0)
+    ref = oracle.crop_and_resize_3d_grad_image(grads[good], boxes[good], bidx[good], image.shape)
+    for bv in (1, 2, 3):
+        rb.custom_op.set_option("car_bwd_variant", bv)
+        gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
+        assert rel_ok(gi, ref, BWD_TOL)
+    gb = rb.crop_and_resize_3d_grad_boxes(t[3], t[0], t[1], t[2]).cpu().numpy()
+    rgb = oracle.crop_and_resize_3d_grad_boxes(grads[good], image, boxes[good], bidx[good])
+    assert np.all(gb[bad] == 0.0)
+    assert np.all(np.abs(gb[good] - rgb) <= GB_TOL * np.abs(rgb).max() + 1e-6)
 
 
 def test_autograd_matches_registered_gradient(rb, cuda_device):

@@ -262,3 +262,21 @@ def test_mask_targets_and_payload_restatements():
     b, _ = oracle.pack_bits(x)
     assert list(b) == [0b01101001, 0b10000000]                               # MSB first, zero padded
     assert oracle.pack_f16(np.array([65520.0, 1e-8, 1.0009765625], np.float32)).tolist() == [np.inf, 0.0, 1.0009765625]
+
+
+def test_restated_tf_image_nms_2d_known_answers():
+    """oracle.non_max_suppression_2d_tf restates tf.image.non_max_suppression (the NMS of this fork's DetectionLayer,
+    core/models.py:1496-1501): strict '>' at the threshold, ties -> lower index, empty boxes never suppress."""
+    b = np.array([[0, 0, 64, 64], [0, 0, 32, 64], [100, 100, 110, 110], [0, 0, 64, 64]], np.float32)
+    s = np.array([0.9, 0.8, 0.7, 0.9], np.float32)
+    assert oracle.non_max_suppression_2d_tf(b, s, 10, 0.5).tolist() == [0, 1, 2]      # IoU(0,1) == 0.5 is not > 0.5; box 3 duplicates 0
+    assert oracle.non_max_suppression_2d_tf(b, s, 10, 0.49).tolist() == [0, 2]
+    assert oracle.non_max_suppression_2d_tf(b, s, 1, 0.5).tolist() == [0]
+    z = np.array([[5, 5, 5, 9], [5, 5, 5, 9]], np.float32)                             # zero-area boxes: IoU 0 with everything
+    assert oracle.non_max_suppression_2d_tf(z, np.array([0.5, 0.4], np.float32), 5, 0.0).tolist() == [0, 1]
+    # agreement with the 3-D op on boxes that share one z interval, away from threshold ties
+    boxes, scores = roi3d_synth.nms_boxes(400, (64, 64, 64), seed=31)
+    boxes[:, 2], boxes[:, 5] = 0.0, 1.0
+    ref3 = oracle.non_max_suppression_3d(boxes, scores, 400, 0.4)
+    ref2 = oracle.non_max_suppression_2d_tf(boxes[:, [1, 0, 4, 3]], scores, 400, 0.4)
+    assert np.array_equal(ref2, ref3)
