@@ -21,4 +21,14 @@ for pkg in crop_and_resize_3d crop_and_resize_3d_grad_image crop_and_resize_3d_g
   cp "$HERE/packages/$pkg.py" "$OUT/$pkg/__init__.py"
 done
 cp "$HERE/packages/_roi3d_loader.py" "$OUT/"
+# ppc64le loader (core/custom_op/ppc64le_custom_op.py:21-30): four libraries, each registering ONE op, under the file
+# names it tf.load_op_library()s.  Copy (or symlink) $OUT/ppc64le/*.so into the reference's core/custom_op/.
+mkdir -p "$OUT/ppc64le"
+n=0
+for lib in crop_and_resize_3d_op crop_and_resize_3d_grad_image_op crop_and_resize_3d_grad_boxes_op non_max_suppression_3d_op; do
+  n=$((n + 1))
+  g++ -std=c++17 -O2 -shared -fPIC "$HERE/roi3d_tf_ops.cc" -o "$OUT/ppc64le/$lib.so" -DROI3D_TF_SINGLE_OP=$n \
+      -I"$ROOT/include" -I"$CUDA_HOME/include" "${TF_CFLAGS[@]}" -DGOOGLE_CUDA=1 \
+      -L"$PKG/lib" -lroi3d_b200 -Wl,-rpath,'$ORIGIN/..' -L"$CUDA_HOME/lib64" -lcudart "${TF_LFLAGS[@]}"
+done
 echo "built: add $OUT to PYTHONPATH (it replaces tensorflow_nms_car_3d-0.1.0)"

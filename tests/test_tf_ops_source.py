@@ -51,3 +51,26 @@ def test_package_shims_export_reference_names():
                        ("crop_and_resize_3d_grad_boxes", "crop_and_resize3d_grad_boxes"), ("non_max_suppression_3d", "non_max_suppression3d")):
         text = open(os.path.join(pk, pkg + ".py")).read()
         assert "%s = _ops.%s" % (pkg, alias) in text
+
+
+@pytest.mark.parametrize("single_op", [None, 1, 2, 3, 4])
+def test_tf_shim_compiles_against_stub_headers(single_op):
+    """g++ -fsyntax-only of the TensorFlow registration against tests/tf_stub (a minimal stand-in for the TF op API with
+    current-TF signatures): removed aliases (tensorflow::OkStatus, tensorflow::int64), typos and wrong argument counts
+    to the C ABI of include/roi3d.h fail here.  ROI3D_TF_SINGLE_OP = 1..4 are the per-op libraries of the ppc64le loader."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    cuda_inc = next((p for p in ("/usr/local/cuda/include",) if os.path.exists(os.path.join(p, "cuda_runtime_api.h"))), None)
+    if cuda_inc is None:
+        pytest.skip("no CUDA headers")
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror=return-type", "-I" + os.path.join(ROOT, "tests", "tf_stub"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + cuda_inc, "-DGOOGLE_CUDA=1", SRC]
+    if single_op:
+        cmd.insert(-1, "-DROI3D_TF_SINGLE_OP=%d" % single_op)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-3000:]
+    src = open(SRC).read()
+    assert "tf::OkStatus" not in src and "tf::int64" not in src          # gone from current TensorFlow
