@@ -413,6 +413,11 @@ def crop_and_resize_3d_grad_image(grads, boxes, box_ind, image_size, T=None, met
     _require(size[4] == gs[4], "image_size and grads are incompatible")
     _require(_shape(boxes)[0] == gs[0], "boxes and grads have incompatible shape")
     dev = _device()
+    if gs[0] == 0 and not any(isinstance(x, torch.Tensor) and x.device.type == "cuda" for x in (grads, boxes, box_ind)):
+        # no boxes, host buffers: the op's result is its zero-fill (GI.so@0x3ec5).  It is produced where the caller
+        # wants it -- in (pinned) host memory -- instead of being memset on the device and carried over PCIe.
+        res = torch.empty(size, dtype=torch.float32, pin_memory=True).zero_()
+        return res.numpy() if isinstance(grads, np.ndarray) or not isinstance(grads, torch.Tensor) else res
     g, b, bi = _Arg(grads, torch.float32, dev), _Arg(boxes, torch.float32, dev), _Arg(box_ind, torch.int32, dev)
     host = g.host or b.host or bi.host
     out = _grad_image_device(g.dev, b.dev, bi.dev, size, method)

@@ -570,24 +570,39 @@ def run_ours(args):
           "grads": torch.from_numpy(op["grads"]).pin_memory()} for op in ops]
     h2d = sum(t.numel() * 4 for t in h_images.values()) + sum(x["grads"].numel() * 4 for x in h) + \
         2 * sum(x["boxes"].numel() * 4 + x["bidx"].numel() * 4 for x in h)
-    d2h = sum(x["grads"].numel() * 4 for x in h) + sum(int(np.prod(op["shape"])) * 4 for op in ops)
+    # crops of every op + grad images of the ops that have boxes (an empty op's zero-filled grad image is produced
+    # directly in host memory by the host-buffer API: nothing crosses PCIe for it)
+    d2h = sum(x["grads"].numel() * 4 for x in h) + sum(int(np.prod(op["shape"])) * 4 for op in ops if op["n"] > 0)
 
-    # The 16 op nodes of a step are independent; like an executor that runs ready nodes first, the step issues the
-    # grad-image nodes of the EMPTY levels first (they need no upload: their zero-filled results start downloading
-    # while the maps are still going up), then the forward nodes, then the grad-image nodes that wait for their grads.
+    # The 16 op nodes of a step are independent; like an executor that runs ready nodes first, the step issues
+    #  1. per pool shape, smallest first: the forward nodes of the levels that received ROIs (their map is uploaded right
+    #     before its first use) and then their grad-image nodes -- so the download engine, which carries more bytes than
+    #     the upload engine, always has a result to move while the next inputs go up,
+    #  2. the forward nodes of the empty levels (their maps are still uploaded: they are inputs of the call),
+    #  3. the grad-image nodes of the EMPTY levels: their result is the op's zero-fill, which the host-buffer API writes
+    #     straight into host memory -- on this thread, while the copies queued above are in flight.
     order_b0 = [i for i, op in enumerate(ops) if op["n"] == 0]
     order_b1 = [i for i, op in enumerate(ops) if op["n"] > 0]
 
     def e2e_step():
         with rb.deferred():
             outs = [None] * (2 * len(ops))
+            d_img = {}
+
+            def dmap(lv):
+                if lv not in d_img:
+                    d_img[lv] = h_images[lv].to(dev, non_blocking=True)
+                return d_img[lv]
+            for crop in sorted(CROPS):
+                for i in order_b1:
+                    if ops[i]["crop"] == crop:      # mixed call: device-resident map, host boxes -> host result
+                        outs[i] = rb.crop_and_resize_3d(dmap(ops[i]["level"]), h[i]["boxes"], h[i]["bidx"], crop)
+                for i in order_b1:
+                    if ops[i]["crop"] == crop:
+                        outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
             for i in order_b0:
-                outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
-            d_img = {lv: t.to(dev, non_blocking=True) for lv, t in h_images.items()}
-            for i, (op, x) in enumerate(zip(ops, h)):
-                # mixed call: device-resident map, host boxes -> host result
-                outs[i] = rb.crop_and_resize_3d(d_img[op["level"]], x["boxes"], x["bidx"], op["crop"])
-            for i in order_b1:
+                outs[i] = rb.crop_and_resize_3d(dmap(ops[i]["level"]), h[i]["boxes"], h[i]["bidx"], ops[i]["crop"])
+            for i in order_b0:                          # host-side zero-fill: runs while the copies above are in flight
                 outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
         return outs
 
@@ -602,6 +617,7 @@ def run_ours(args):
             e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
+    e2e_by_rank = rb.sharding.gather_over_ranks(e2e_s)
     e2e_s = rb.sharding.max_over_ranks(e2e_s)
     e2e_value = world * total_rois * e2e_steps / e2e_s
 
@@ -640,7 +656,13 @@ def run_ours(args):
         "hbm_gbs_step": round(step_gbs, 1), "hbm_frac_step": round(step_gbs / peak, 4),
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3)},
+                "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3),
+                "ms_per_step_by_rank": [round(v / e2e_steps * 1e3, 2) for v in e2e_by_rank],
+                "pcie_gbs_by_rank": [{"h2d": round(h2d * e2e_steps / v / 1e9, 1), "d2h": round(d2h * e2e_steps / v / 1e9, 1)}
+                                     for v in e2e_by_rank] if not args.no_e2e else None,
+                "note": "host buffers in / host results out; both copy directions run concurrently, so each rate is bytes of that "
+                        "direction / whole step time (single-GPU ceilings of this pool: 55 GB/s one way, 47 GB/s each way "
+                        "when both are busy, profiles/pcie_probe.py)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "nms3d": nms,

@@ -263,6 +263,10 @@ def test_car_empty_and_single(rb, cuda_device):
     gi = rb.crop_and_resize_3d_grad_image(g, e6, ei, (1, 4, 4, 4, 8))
     assert tuple(gi.shape) == (1, 4, 4, 4, 8) and float(gi.abs().sum()) == 0.0     # zero-filled like GI.so@0x3ec5
     assert tuple(rb.crop_and_resize_3d_grad_boxes(g, image, e6, ei).shape) == (0, 6)
+    # host buffers, no boxes: the zero-filled result is produced in host memory (numpy in -> numpy out)
+    hz = rb.crop_and_resize_3d_grad_image(np.zeros((0, 7, 7, 7, 8), np.float32), np.zeros((0, 6), np.float32),
+                                          np.zeros(0, np.int32), (2, 4, 4, 4, 8))
+    assert isinstance(hz, np.ndarray) and hz.shape == (2, 4, 4, 4, 8) and hz.dtype == np.float32 and not hz.any()
 
 
 @pytest.mark.parametrize("case", [CAR_CASES[0], CAR_CASES[1], CAR_CASES[7]])
