@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libroi3d_b200.so")
 HEADER = os.path.join(_ROOT, "include", "roi3d.h")
 
-SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_car_os.cu", "roi3d_nms.cu", "roi3d_boxes.cu",
+SOURCES = ["roi3d_abi.cu", "roi3d_car_direct.cu", "roi3d_car_plane.cu", "roi3d_car_sep.cu", "roi3d_car_os.cu", "roi3d_nms.cu", "roi3d_boxes.cu",
            "roi3d_detect.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",      # Blackwell B200 only

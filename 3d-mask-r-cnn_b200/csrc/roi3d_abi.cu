@@ -59,6 +59,8 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_os_stage_kib")) return OPT_OS_STAGE_KIB;
     if (!strcmp(name, "car_os_debug")) return OPT_OS_DEBUG;
     if (!strcmp(name, "car_bwd_image_split")) return OPT_BWD_SPLIT;
+    if (!strcmp(name, "car_sep_rows")) return OPT_SEP_RC;
+    if (!strcmp(name, "car_sep_ring")) return OPT_SEP_NS;
     return -1;
 }
 
@@ -152,6 +154,11 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
     // has enough outputs to amortise its per-CTA tables -- from 10 x 10 at any channel count >= 32, from 7 x 7 when
     // the channel chunks are full (C >= 128); below that the direct gather wins or ties
     if (variant == 0) variant = (plane_ok && ((C >= 32 && ph * pw >= 100) || (C >= 128 && ph * pw >= 49))) ? 2 : 1;
+    if (variant == 4 && plane_ok) {                                     // row-walk separable kernel
+        const int rc = launch_car3d_fwd_sep(image, boxes, box_index, g, extrapolation_value, crops, nullptr, false, s);
+        if (rc != ROI3D_EUNSUPPORTED) return rc;
+        variant = 2;
+    }
     if (variant == 3 && plane_ok) {                                     // TMA-fed plane kernel (opt-in)
         const int rc = launch_car3d_fwd_plane_tma(image, boxes, box_index, g, extrapolation_value, crops, s);
         if (rc != ROI3D_EUNSUPPORTED) return rc;

@@ -18,7 +18,8 @@ extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
 enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_PDL = 6,
-       OPT_OS_TZ = 7, OPT_OS_STAGES = 8, OPT_OS_STAGE_KIB = 9, OPT_OS_DEBUG = 10, OPT_BWD_SPLIT = 11, OPT_COUNT };
+       OPT_OS_TZ = 7, OPT_OS_STAGES = 8, OPT_OS_STAGE_KIB = 9, OPT_OS_DEBUG = 10, OPT_BWD_SPLIT = 11, OPT_SEP_RC = 12, OPT_SEP_NS = 13,
+       OPT_COUNT };
 // cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, device, size) instead of on every call
 cudaError_t ensure_dyn_smem(const void *kernel, size_t bytes);
 // multiprocessor count of the current device (cached per device)
@@ -182,6 +183,9 @@ int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *bo
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
                                   float *grad_image, cudaStream_t stream, bool zero_fill = false);
+struct PyrParams;
+int launch_car3d_fwd_sep(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                         float ext, void *crops, const PyrParams *pyr, bool half_out, cudaStream_t stream);
 bool car3d_grad_image_os_supported(const CarGeom &g);
 long long car3d_grad_image_os_ctas(const CarGeom &g);
 int launch_car3d_grad_image_os(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
