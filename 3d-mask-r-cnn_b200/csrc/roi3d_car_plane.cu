@@ -838,7 +838,10 @@ zero_fill_kernel(float4 *__restrict__ p, size_t n4)
 {
     pdl_trigger();
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) { p[i] = z; p[i + stride] = z; }
+    if (i < n4) p[i] = z;
 }
 
 struct Fill4 { float4 *p[4]; size_t n4[4]; };
@@ -853,8 +856,18 @@ zero_fill4_kernel(const Fill4 f)
     for (int r = 3; r >= 0; --r) {                              // coarsest level first: the largest map (P2, most ROIs) is the
         float4 *p = f.p[r];                                     // most recently written one when the scatter kernel starts
         const size_t n4 = f.n4[r];
-        for (size_t i = t0; i < n4; i += stride) p[i] = z;
+        size_t i = t0;
+        for (; i + stride < n4; i += 2 * stride) { p[i] = z; p[i + stride] = z; }
+        if (i < n4) p[i] = z;
     }
+}
+
+// CTAs per SM of the zero-fill kernels.  They need few registers and no shared memory, so a fill grid that does not
+// occupy every thread slot lets CTAs of the PDL-launched scatter kernel become resident next to it and run their
+// prologue (tables, first grads slice) while the zeros are written (option "car_fill_ctas_per_sm").
+static inline unsigned fill_grid() {
+    const int per_sm = option_value(OPT_FILL_CTAS) > 0 ? option_value(OPT_FILL_CTAS) : 8;
+    return (unsigned)(num_sms() * per_sm);
 }
 
 static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
@@ -870,7 +883,13 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
     for (;;) {
         const size_t eb = (size_t)L.cl * V * 16;
         // stage whole k-slices when they fit ~50 KB, else tile over y samples
-        L.zcap = max(g.pw, min(g.ph * g.pw, (int)(((V == 1 ? 50 : 64) * 1024) / eb)));
+        const int kib = option_value(OPT_BWD_STAGE_KIB) > 0 ? option_value(OPT_BWD_STAGE_KIB) : (V == 1 ? 50 : 64);
+        L.zcap = max(g.pw, min(g.ph * g.pw, (int)((kib * 1024) / eb)));
+        {   // equal y-tiles: 14 sample rows at a capacity of 9 become 7 + 7 instead of 9 + 5 (-2 % at cfg2 14^3,
+            // profiles/bwd_stage_sweep.py) and the CTA asks for no more shared memory than its tiles use
+            const int ty = max(1, L.zcap / g.pw), nt = (g.ph + ty - 1) / ty;
+            L.zcap = ((g.ph + nt - 1) / nt) * g.pw;
+        }
         smem = fixed + (size_t)L.zcap * eb;
         if (smem <= 200 * 1024) break;
         if (V > 1) V = 1; else if (L.cl > 1) L.cl /= 2; else return ROI3D_EUNSUPPORTED;
@@ -892,7 +911,7 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
         for (int img = 0; img < (split ? g.B : 1); ++img) {
             const size_t n4 = (split ? per_image : per_image * g.B) / 16;
             float *dst = grad_image + (split ? (size_t)img * (per_image / 4) : 0);
-            zero_fill_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
+            zero_fill_kernel<<<fill_grid(), 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
             ROI3D_LAUNCH_CHECK();
             ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
                                             grad_image, PyrParams{}, split ? img : -1));
@@ -948,7 +967,7 @@ int launch_pyramid_grad(const float *grads, float *const grad_images[4], const i
     const CarGeom g{B, H[0], wmax, D[0], C, B * rois_per_image, ph, pw, pd};
     // one zero-fill kernel for the four maps; the scatter kernel behind it is launched with programmatic dependent
     // launch and waits (griddepcontrol.wait) only before its first RED (option "pdl" = 1: plain stream order)
-    zero_fill4_kernel<<<num_sms() * 8, 256, 0, stream>>>(f);
+    zero_fill4_kernel<<<fill_grid(), 256, 0, stream>>>(f);
     ROI3D_LAUNCH_CHECK();
     if (g.n == 0) return ROI3D_OK;
     return launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream, false, option_value(OPT_PDL) == 0);
