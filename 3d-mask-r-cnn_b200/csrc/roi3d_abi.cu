@@ -61,6 +61,7 @@ static int option_index(const char *name) {
     if (!strcmp(name, "car_bwd_image_split")) return OPT_BWD_SPLIT;
     if (!strcmp(name, "car_fill_ctas_per_sm")) return OPT_FILL_CTAS;
     if (!strcmp(name, "car_bwd_stage_kib")) return OPT_BWD_STAGE_KIB;
+    if (!strcmp(name, "car_experiment")) return OPT_EXPERIMENT;         // bit mask of A/B switches used by profiles/*.py
     if (!strcmp(name, "car_sep_rows")) return OPT_SEP_RC;
     if (!strcmp(name, "car_sep_ring")) return OPT_SEP_NS;
     return -1;

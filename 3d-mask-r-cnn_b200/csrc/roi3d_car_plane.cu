@@ -180,7 +180,9 @@ struct __align__(16) OutEntry {             // per output (y, x) of the current 
 // ---------------------------------------------------------------------------------
 // forward.  V = float4 channel groups per thread (the chunk is cl * V * 4 channels).
 // ---------------------------------------------------------------------------------
-template <int V, bool PYR, bool HALF = false>
+// FULL: every channel lane of every chunk carries live channels ((C / 4) % (cl * V) == 0, e.g. C = 256): the per-group
+// predicates, and the divergence bookkeeping (BSSY / BSYNC) they drag into every inner loop, compile away.
+template <int V, bool PYR, bool HALF = false, bool FULL = false>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                        const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
@@ -230,7 +232,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const int c4 = chunk * cl * V + lane;                   // first float4 channel group of this thread
     bool von[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
+    for (int v = 0; v < V; ++v) von[v] = FULL || (c4 + v * cl) < g.C / 4;
     const unsigned sW = (unsigned)g.D * g.C, sH = (unsigned)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_index + b);
     const bool bad_img = (unsigned)bimg >= (unsigned)g.B;     // out-of-range box_index: the whole crop extrapolates, nothing is read
@@ -572,7 +574,7 @@ __device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, c
     __syncthreads();
 }
 
-template <int V, bool PYR>
+template <int V, bool PYR, bool FULL = false>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
@@ -623,7 +625,7 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
     const int c4 = chunk * cl * V + lane;
     bool von[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) von[v] = (c4 + v * cl) < g.C / 4;
+    for (int v = 0; v < V; ++v) von[v] = FULL || (c4 + v * cl) < g.C / 4;
     const long long sW = (long long)g.D * g.C, sH = (long long)g.W * g.D * g.C;
     const int bimg = PYR ? b / P.rois_per_image : __ldg(box_ind + b);
     if ((unsigned)bimg >= (unsigned)g.B) return;             // out-of-range box_ind (CTA-uniform): nothing is scattered
@@ -786,9 +788,15 @@ static int launch_fwd_plane_impl(const float *image, const float *boxes, const i
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
     if (half_out && !pyr) return ROI3D_EUNSUPPORTED;           // float16 output exists for the fused pyramid forward only
-    auto kern = half_out ? ((V == 2) ? car3d_fwd_plane_kernel<2, true, true> : car3d_fwd_plane_kernel<1, true, true>)
-              : pyr ? ((V == 2) ? car3d_fwd_plane_kernel<2, true> : car3d_fwd_plane_kernel<1, true>)
-                    : ((V == 2) ? car3d_fwd_plane_kernel<2, false> : car3d_fwd_plane_kernel<1, false>);
+    const bool full = (g.C / 4) % (L.cl * V) == 0 && !(option_value(OPT_EXPERIMENT) & 1);
+    using K = void (*)(const float *, const float *, const int *, CarGeom, PlaneLaunch, float, void *, const PyrParams);
+    K kern;
+    if (V == 2) kern = half_out ? (full ? (K)car3d_fwd_plane_kernel<2, true, true, true> : (K)car3d_fwd_plane_kernel<2, true, true, false>)
+                     : pyr      ? (full ? (K)car3d_fwd_plane_kernel<2, true, false, true> : (K)car3d_fwd_plane_kernel<2, true, false, false>)
+                                : (full ? (K)car3d_fwd_plane_kernel<2, false, false, true> : (K)car3d_fwd_plane_kernel<2, false, false, false>);
+    else        kern = half_out ? (full ? (K)car3d_fwd_plane_kernel<1, true, true, true> : (K)car3d_fwd_plane_kernel<1, true, true, false>)
+                     : pyr      ? (full ? (K)car3d_fwd_plane_kernel<1, true, false, true> : (K)car3d_fwd_plane_kernel<1, true, false, false>)
+                                : (full ? (K)car3d_fwd_plane_kernel<1, false, false, true> : (K)car3d_fwd_plane_kernel<1, false, false, false>);
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
@@ -885,7 +893,7 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
         // stage whole k-slices when they fit ~50 KB, else tile over y samples
         const int kib = option_value(OPT_BWD_STAGE_KIB) > 0 ? option_value(OPT_BWD_STAGE_KIB) : (V == 1 ? 50 : 64);
         L.zcap = max(g.pw, min(g.ph * g.pw, (int)((kib * 1024) / eb)));
-        {   // equal y-tiles: 14 sample rows at a capacity of 9 become 7 + 7 instead of 9 + 5 (-2 % at cfg2 14^3,
+        if (!(option_value(OPT_EXPERIMENT) & 4)) {   // equal y-tiles: 14 sample rows at a capacity of 9 become 7 + 7 instead of 9 + 5 (-2 % at cfg2 14^3,
             // profiles/bwd_stage_sweep.py) and the CTA asks for no more shared memory than its tiles use
             const int ty = max(1, L.zcap / g.pw), nt = (g.ph + ty - 1) / ty;
             L.zcap = ((g.ph + nt - 1) / nt) * g.pw;
@@ -896,8 +904,15 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
     }
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
-    auto kern = pyr ? ((V == 2) ? car3d_grad_image_plane_kernel<2, true> : car3d_grad_image_plane_kernel<1, true>)
-                    : ((V == 2) ? car3d_grad_image_plane_kernel<2, false> : car3d_grad_image_plane_kernel<1, false>);
+    // FULL pays off in the pyramid instantiation only (cfg2 14^3: 0.377 vs 0.398 ms); in the plain one ptxas then spills
+    // inside the gather loop (0.398 vs 0.371 ms) -- measured with profiles/full_ab.py (car_experiment bit 2 flips the choice)
+    const bool full = (g.C / 4) % (L.cl * V) == 0 && ((pyr != nullptr) != ((option_value(OPT_EXPERIMENT) & 2) != 0));
+    using K = void (*)(const float *, const float *, const int *, CarGeom, PlaneLaunch, float *, const PyrParams, const int);
+    K kern;
+    if (V == 2) kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<2, true, true> : (K)car3d_grad_image_plane_kernel<2, true, false>)
+                           : (full ? (K)car3d_grad_image_plane_kernel<2, false, true> : (K)car3d_grad_image_plane_kernel<2, false, false>);
+    else        kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<1, true, true> : (K)car3d_grad_image_plane_kernel<1, true, false>)
+                           : (full ? (K)car3d_grad_image_plane_kernel<1, false, true> : (K)car3d_grad_image_plane_kernel<1, false, false>);
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;

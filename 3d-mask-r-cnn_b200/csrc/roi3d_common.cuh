@@ -18,7 +18,7 @@ extern thread_local int g_last_cuda_error;
 extern thread_local long long g_launches;
 int option_value(int which);
 enum { OPT_CAR_FWD_VARIANT = 0, OPT_CAR_BWD_VARIANT = 1, OPT_NMS_VARIANT = 2, OPT_CAR_V = 3, OPT_KSPLIT = 4, OPT_NMS_SORT = 5, OPT_PDL = 6,
-       OPT_OS_TZ = 7, OPT_OS_STAGES = 8, OPT_OS_STAGE_KIB = 9, OPT_OS_DEBUG = 10, OPT_BWD_SPLIT = 11, OPT_SEP_RC = 12, OPT_SEP_NS = 13, OPT_FILL_CTAS = 14, OPT_BWD_STAGE_KIB = 15,
+       OPT_OS_TZ = 7, OPT_OS_STAGES = 8, OPT_OS_STAGE_KIB = 9, OPT_OS_DEBUG = 10, OPT_BWD_SPLIT = 11, OPT_SEP_RC = 12, OPT_SEP_NS = 13, OPT_FILL_CTAS = 14, OPT_BWD_STAGE_KIB = 15, OPT_EXPERIMENT = 16,
        OPT_COUNT };
 // cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, device, size) instead of on every call
 cudaError_t ensure_dyn_smem(const void *kernel, size_t bytes);
