@@ -108,6 +108,97 @@ def run_cfg4(torch, rb, lib, dev, world, peak, ptr, stream, barrier):
             "bwd_ms": round(t_b, 4), "bwd_frac": round(bb / (t_b * 1e-3) / 1e9 / peak, 4)}
 
 
+def run_mixed_levels(torch, rb, lib, dev, images, ptr, stream):
+    """PyramidROIAlign where the ROIs spread over the levels (sides 32-128 px -> P2/P3/P4): the drop-in path (host
+    routing, one op call per level, crops gathered back into ROI order = what core/models.py:663-683 executes) against
+    the fused entry points.  Both legs are CUDA-graph replays of forward + backward for the 7^3 and 14^3 pools."""
+    vp = ctypes.c_void_p
+    R = ROIS_PER_IMAGE
+    boxes_br = np.stack([roi3d_synth.rois(R, VOLUME, 7000 + b, side_px=(32.0, 128.0)) for b in range(BATCH)])
+    flat = boxes_br.reshape(-1, 6)
+    bidx_all = np.repeat(np.arange(BATCH, dtype=np.int32), R)
+    lv = roi3d_synth.roi_levels(flat, VOLUME)
+    fms = [images[l] for l in roi3d_synth.LEVELS]
+    C = fms[0].shape[4]
+    d_boxes_br = torch.from_numpy(boxes_br).to(dev)
+    per_level = []
+    for li, level in enumerate(roi3d_synth.LEVELS):
+        sel = np.nonzero(lv == level)[0]
+        per_level.append({"n": len(sel), "sel": torch.from_numpy(sel).to(dev), "fm": fms[li],
+                          "boxes": torch.from_numpy(np.ascontiguousarray(flat[sel])).to(dev),
+                          "bidx": torch.from_numpy(np.ascontiguousarray(bidx_all[sel])).to(dev),
+                          "gimg": {c: torch.empty_like(fms[li]) for c in CROPS}})
+    order = torch.argsort(torch.cat([pl["sel"] for pl in per_level]))       # level-sorted rows -> ROI order
+    crops_lv = {c: torch.empty((BATCH * R,) + c + (C,), device=dev) for c in CROPS}      # level-sorted crops
+    pooled = {c: torch.empty((BATCH * R,) + c + (C,), device=dev) for c in CROPS}        # ROI order (the layer's output)
+    grads = {c: torch.randn((BATCH * R,) + c + (C,), device=dev) for c in CROPS}         # ROI order (the layer's input gradient)
+    grads_lv = {c: torch.empty_like(grads[c]) for c in CROPS}
+    inv = torch.cat([pl["sel"] for pl in per_level])
+
+    def per_op_step(glue):
+        for c in CROPS:
+            off = 0
+            for pl in per_level:
+                B_, H, W, D, _ = pl["fm"].shape
+                out = crops_lv[c][off:off + pl["n"]]
+                rb._lib.check(lib.roi3d_car3d_fwd(ptr(pl["fm"]), B_, H, W, D, C, ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"],
+                                                  c[0], c[1], c[2], 0, 0.0, vp(out.data_ptr()), stream()))
+                off += pl["n"]
+            if glue:
+                torch.index_select(crops_lv[c], 0, order, out=pooled[c])        # tf.gather(pooled, ix), core/models.py:675-683
+        for c in CROPS:
+            if glue:
+                torch.index_select(grads[c], 0, inv, out=grads_lv[c])           # its gradient: rows back into level order
+            src = grads_lv[c] if glue else grads[c]
+            off = 0
+            for pl in per_level:
+                B_, H, W, D, _ = pl["fm"].shape
+                gin = src[off:off + pl["n"]]
+                rb._lib.check(lib.roi3d_car3d_grad_image(vp(gin.data_ptr()), ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"], c[0], c[1], c[2],
+                                                         B_, H, W, D, C, 0, ptr(pl["gimg"][c]), stream()))
+                off += pl["n"]
+
+    lshapes = (ctypes.c_int * 12)(*[int(d) for fm in fms for d in fm.shape[1:4]])
+    ishape = (ctypes.c_float * 3)(*[float(v) for v in VOLUME])
+    fm_ptrs = (vp * 4)(*[fm.data_ptr() for fm in fms])
+    gm_ptrs = {c: (vp * 4)(*[pl["gimg"][c].data_ptr() for pl in per_level]) for c in CROPS}
+
+    def fused_step():
+        for c in CROPS:
+            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), R, ishape, c[0], c[1], c[2],
+                                                          ptr(pooled[c]), stream()))
+        for c in CROPS:
+            rb._lib.check(lib.roi3d_pyramid_roi_align_grad(ptr(grads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br), R, ishape,
+                                                           c[0], c[1], c[2], stream()))
+
+    def graph_ms(fn, reps=20):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        for _ in range(3):
+            gr.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    res = {"rois_per_level": {"P%d" % l: pl["n"] for l, pl in zip(roi3d_synth.LEVELS, per_level)},
+           "per_op_ms": round(graph_ms(lambda: per_op_step(False)), 4),
+           "per_op_with_reorder_ms": round(graph_ms(lambda: per_op_step(True)), 4),
+           "fused_ms": round(graph_ms(fused_step), 4),
+           "note": "ROI sides 32-128 px; per_op = one C-ABI call per level and pool, crops left in level order; "
+                   "per_op_with_reorder adds the layer's tf.gather back into ROI order and its gradient (torch.index_select "
+                   "stands in for the TF glue); fused = roi3d_pyramid_roi_align_fwd/grad (routing and order restore inside)"}
+    return res
+
+
 def set_workload(name):
     """cfg2 (default, BASELINE configs[1]) or cfg4 (configs[3]: mask-head stress, 1000 ROIs x 14^3 x 256 ch, one image per GPU)."""
     global BATCH, ROIS_PER_IMAGE, CROPS, WORKLOAD, WORKLOAD_NAME
@@ -398,6 +489,12 @@ def run_ours(args):
                      "zero-fill kernel for the four grad maps; same launch mode (CUDA graph replay) as the per-op step"}
     if not args.no_graph:
         del fgraph
+    if WORKLOAD_NAME == "cfg2" and not args.no_graph:
+        try:
+            fused["mixed_levels"] = run_mixed_levels(torch, rb, lib, dev, images, ptr, stream)
+        except torch.cuda.OutOfMemoryError:
+            fused["mixed_levels"] = {"skipped": "out of memory"}
+        torch.cuda.empty_cache()
     # float16 output (the target files' payload) written by the crop kernel vs float32 crop + separate conversion
     f16 = {}
     for c in CROPS:
