@@ -252,18 +252,23 @@ ROI3D_API int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y
 
 /* ---------------------------------------------------------------------------
  * Tuning / introspection (not part of the reference surface).
- * roi3d_set_option: process-wide knobs used by the benchmarks and tests to
- * select a kernel variant; the defaults are the production choice.
+ * roi3d_set_option: knobs of the CALLING THREAD (thread-local; another thread's calls are unaffected), used by the
+ * benchmarks and tests to select a kernel variant; the defaults (0) are the production choice.
  *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable, 3 = plane-staged fed by TMA bulk
- *                       copies (bit-exact, slower at the row sizes of this path; opt-in)
- *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged separable
- *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane kernels
- *   "nms_variant"       0 = speculative head/tail schedule, 1 = single phase (full mask, then one scan)
- *   "nms_pdl"           0 = the mask / scan kernels are launched with programmatic dependent launch (their launch
- *                       latency overlaps the predecessor), 1 = plain stream order
- *   "nms_sort_variant"  0 = auto (bucketed from 8192 boxes), 1 = rank by counting, 2 = bucketed sort
+ *                       copies, 4 = row-walk separable (z / x / y lerps each evaluated once); 3 and 4 are bit-exact
+ *                       but slower at the row sizes of this path: opt-in
+ *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged RED scatter, 3 = output-stationary (every
+ *                       voxel stored once, no zero-fill, no atomics, deterministic; slower: opt-in)
+ *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane / row-walk kernels
  *   "car_ctas_per_sm_target"   grid sizing of the plane kernels: depth-sample splits are chosen so that about this
  *                       many CTAs per SM exist (0 = default 16)
+ *   "pdl" (alias "nms_pdl")    0 = dependent kernels (NMS mask / scan chain, grad-image scatter behind its zero-fill)
+ *                       are launched with programmatic dependent launch, 1 = plain stream order
+ *   "nms_variant"       0 = speculative head/tail schedule, 1 = single phase (full mask, then one scan)
+ *   "nms_sort_variant"  0 = auto (bucketed from 8192 boxes), 1 = rank by counting, 2 = bucketed sort
+ *   experiment knobs read by profiles/*.py only: "car_os_tile_depth", "car_os_ring_stages", "car_os_stage_kib",
+ *   "car_os_debug", "car_bwd_image_split", "car_sep_rows", "car_sep_ring", "car_fill_ctas_per_sm",
+ *   "car_bwd_stage_kib", "car_experiment"
  * Returns ROI3D_EINVAL for an unknown name.  roi3d_kernel_launches() returns
  * the number of kernel launches this library has enqueued on the calling
  * thread since the last roi3d_reset_kernel_launches().
