@@ -239,6 +239,43 @@ def test_car_grad_boxes_matches_oracle(rb, cuda_device, case):
     assert np.all(np.abs(out - ref) <= GB_TOL * np.abs(ref).max() + 1e-6)
 
 
+def _fuzz_case(seed):
+    """Random geometry: ragged volumes, crops up to 20 per axis (non-cubic), any channel count (C % 4 != 0 included),
+    boxes partly / fully outside, reversed, degenerate, on integer coordinates; random extrapolation value."""
+    rng = np.random.default_rng(seed)
+    B = int(rng.integers(1, 4))
+    H, W, D = (int(rng.integers(1, 20)) for _ in range(3))
+    C = int(rng.choice([1, 3, 4, 8, 20, 36, 64, 68, 132, 256]))
+    crop = tuple(int(rng.integers(1, 21)) for _ in range(3))
+    n = int(rng.integers(1, 14))
+    image = rng.standard_normal((B, H, W, D, C), dtype=np.float32)
+    c = rng.uniform(-0.2, 1.2, (n, 3))
+    side = rng.uniform(0.0, 1.3, (n, 3)) * rng.choice([1.0, 1.0, 1.0, -1.0], (n, 3))      # some corners reversed
+    boxes = np.concatenate([c - side / 2, c + side / 2], axis=1).astype(np.float32)
+    for i in range(0, n, 5):                                                              # integer-coordinate boxes
+        boxes[i] = np.array([0, 0, 0, 1, 1, 1], np.float32) * rng.choice([0.5, 1.0])
+    bidx = rng.integers(0, B, n).astype(np.int32)
+    grads = rng.standard_normal((n,) + crop + (C,), dtype=np.float32)
+    return image, boxes, bidx, grads, crop, float(rng.choice([0.0, -3.5, 0.25]))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_car_fuzz_all_variants(rb, cuda_device, seed):
+    """Every forward variant bit-exact and every backward variant within 1e-4 of the oracle on random geometry."""
+    image, boxes, bidx, grads, crop, ext = _fuzz_case(7000 + seed)
+    ref = oracle.crop_and_resize_3d(image, boxes, bidx, crop, "trilinear", ext)
+    gref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape)
+    t = [dev(x, cuda_device) for x in (image, boxes, bidx, grads)]
+    for fv in (0, 1, 2, 3, 4):
+        rb.custom_op.set_option("car_fwd_variant", fv)
+        out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=ext).cpu().numpy()
+        assert np.array_equal(out, ref), ("forward variant", fv, image.shape, crop)
+    for bv in (0, 1, 2, 3):
+        rb.custom_op.set_option("car_bwd_variant", bv)
+        gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
+        assert rel_ok(gi, gref, BWD_TOL), ("backward variant", bv, image.shape, crop)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "car_*.npz"))))
 def test_car_golden(rb, cuda_device, path):
     z = np.load(path)
