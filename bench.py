@@ -898,6 +898,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not args.reference_child:
+        # The measurement runs in a locked-down child (no file writes, no network: it executes the reference wheel's
+        # machine code); this process only relays the child's JSON line, so the line reaches stdout whether stdout is
+        # a pipe, a terminal or a file (RLIMIT_FSIZE = 0 in the child would turn a redirected print into EFBIG).
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--reference-child", "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            sys.stderr.write(res.stderr[-2000:])
+            raise SystemExit("reference arm failed (child exit code %d)" % res.returncode)
+        print(lines[-1])
+        return
     oracle, ref = _cpu_engines()
     kind = "reference" if ref is not None else "port"
     if ref is not None:                                 # this process only ever runs the reference: lock it down
@@ -944,6 +957,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the extra BASELINE configs[3] measurement")
     ap.add_argument("--cpu-baseline-child", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--reference-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     set_workload(args.workload)
     if args.cpu_baseline_child:
