@@ -48,6 +48,7 @@ from .custom_op import (        # noqa: E402,F401
     set_option,
     unpack_bits,
     unpack_f16,
+    upload,
 )
 
 __version__ = "0.1.0"

@@ -347,12 +347,18 @@ __device__ __forceinline__ bool iou_ge(const float4 a0, const float4 a1, const f
 template <int ROWS>
 __global__ void __launch_bounds__(MK_WARPS * 32)
 nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, float thr,
-                int word_begin, int row_end, const ScanState *__restrict__ state, unsigned *__restrict__ mask)
+                int word_begin, int row_end, const ScanState *__restrict__ state, unsigned *__restrict__ mask,
+                const int *__restrict__ krows, int known_rows)
 {
     // The grid covers mask words [word_begin, ...) of rows [0, row_end): the head phase computes the top-left
     // triangle (word_begin = 0, row_end = T), the tail phase everything right of it (word_begin = T / 32, all rows) --
     // unless the head phase's scan already finished (state->done), which is the common case when max_out << n.
+    // Rows below `known_rows` were already visited by the scans of the earlier phases: the scan will only ever read
+    // the rows it KEPT (their positions are in krows[0 .. state.nsel)), so the mask words of the suppressed ones are
+    // not computed at all -- with dense proposals (what a trained RPN produces) that is most of the rows above a tail
+    // window (6000 dense boxes: 1536 x 4464 pairs shrink to ~250 x 4464).  The skipped words keep whatever the workspace held.
     __shared__ float4 s_rows[ROWS * 2];
+    __shared__ unsigned s_kept[ROWS / 32];
     pdl_wait();                                                          // predecessor (sort / head scan) complete
     pdl_trigger();
     const int z = blockIdx.z, n = min(seg_size(seg, z), row_end);
@@ -366,6 +372,19 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
     if ((w0 + MK_WARPS) * 32 <= i0) return;
     const int ncol = seg_size(seg, z);
     const int rows = min(ROWS, n - i0);
+    const bool use_kept = known_rows > 0 && i0 < known_rows;             // CTA-uniform
+    if (use_kept) {
+        if (threadIdx.x < ROWS / 32) s_kept[threadIdx.x] = 0u;
+        __syncthreads();
+        const int nsel = state[z].nsel;
+        const int *kr = krows + (size_t)z * seg.stride;
+        for (int q = threadIdx.x; q < nsel; q += blockDim.x) {
+            const int r = __ldg(kr + q) - i0;
+            if (r >= 0 && r < ROWS) atomicOr(&s_kept[r >> 5], 1u << (r & 31));
+        }
+        if (threadIdx.x < ROWS && i0 + (int)threadIdx.x >= known_rows)     // rows of this block the scans have not reached yet
+            atomicOr(&s_kept[threadIdx.x >> 5], 1u << (threadIdx.x & 31));
+    }
     for (int t = threadIdx.x; t < rows * 2; t += blockDim.x)
         s_rows[t] = __ldg(reinterpret_cast<const float4 *>(sboxes + i0) + t);
     __syncthreads();
@@ -383,15 +402,18 @@ nms_mask_kernel(const SBox *__restrict__ sboxes, NmsSeg seg, int pitch_words, fl
     for (int rb = 0; rb < rows; rb += 32) {
         // rows whose word lies entirely below the diagonal are never read
         if ((w + 1) * 32 <= i0 + rb) continue;
+        const unsigned kw = use_kept ? s_kept[rb >> 5] : 0xFFFFFFFFu;    // rows of this group the scan can still read
+        if (kw == 0u) continue;
         unsigned word = 0;
         const int rend = min(32, rows - rb);
 #pragma unroll 8
         for (int r = 0; r < rend; ++r) {
+            if (!((kw >> r) & 1u)) continue;                             // warp-uniform
             const bool bit = iou_ge(s_rows[2 * (rb + r)], s_rows[2 * (rb + r) + 1], b0, b1, thr) && !pad_bit;
             const unsigned wd = __ballot_sync(0xffffffffu, bit);
             if (lane == r) word = wd;
         }
-        if (lane < rend) mask[(size_t)(i0 + rb + lane) * pitch_words + w] = word;
+        if (lane < rend && ((kw >> lane) & 1u)) mask[(size_t)(i0 + rb + lane) * pitch_words + w] = word;
     }
 }
 
@@ -746,11 +768,12 @@ int launch_nms3d(const float *boxes, const float *scores, const int *seg_offsets
         if (ph == 0 && nphase > 1) {                           // a small head triangle needs more, smaller CTAs
             dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (c1 + 31) / 32, S);
             ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<32>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
-                                            L.pitch_words, thr, wb, c1, st, mask));
+                                            L.pitch_words, thr, wb, c1, st, mask, (const int *)krows, 0));
         } else {
             dim3 mgrid((words + MK_WARPS - 1) / MK_WARPS, (c1 + MK_ROWS - 1) / MK_ROWS, S);
             ROI3D_CUDA_TRY(launch_dependent(nms_mask_kernel<MK_ROWS>, mgrid, dim3(MK_WARPS * 32), 0, stream, pdl, (const SBox *)sboxes, seg,
-                                            L.pitch_words, thr, wb, c1, st, mask));
+                                            L.pitch_words, thr, wb, c1, st, mask, (const int *)krows,
+                                            (ph > 0 && option_value(OPT_EXPERIMENT) != 8) ? c0 : 0));
         }
         ROI3D_LAUNCH_CHECK();
         ROI3D_CUDA_TRY(launch_dependent(nms_scan_kernel, dim3(S), dim3(SC_THREADS), smem, stream, pdl, (const unsigned *)mask, L.pitch_words,

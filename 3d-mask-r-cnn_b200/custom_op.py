@@ -35,7 +35,7 @@ __all__ = [
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
     "non_max_suppression_3d_batched", "non_max_suppression_3d_per_class", "non_max_suppression_3d_graph",
     "pyramid_roi_align_3d", "PyramidROIAlign3DFunction", "overlaps_3d", "decode_proposals", "top_k_set", "proposal_layer",
-    "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize",
+    "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize", "upload",
 ]
 
 METHODS = {"trilinear": 0, "nearest": 1}
@@ -144,6 +144,14 @@ class _Arg:
             if t.dtype != dtype:
                 t = t.to(dtype)
             self.dev = t.contiguous()
+
+
+def upload(x, dtype=torch.float32):
+    """Bring a host tensor / array to the current device through the host-buffer pipeline's upload stream, in order
+    with the uploads of the op calls around it (uploads issued from different streams share the copy engine and delay
+    each other); returns a device tensor that is ready on the current stream.  For inputs several op calls share --
+    PyramidROIAlign's feature maps feed the 7^3 and the 14^3 crop."""
+    return _Arg(x, dtype, _device()).dev
 
 
 def _finish(out, host, as_numpy):

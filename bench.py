@@ -672,9 +672,12 @@ def run_ours(args):
     d2h = sum(x["grads"].numel() * 4 for x in h) + sum(int(np.prod(op["shape"])) * 4 for op in ops if op["n"] > 0)
 
     # The 16 op nodes of a step are independent; like an executor that runs ready nodes first, the step issues
-    #  1. per pool shape, smallest first: the forward nodes of the levels that received ROIs (their map is uploaded right
-    #     before its first use) and then their grad-image nodes -- so the download engine, which carries more bytes than
-    #     the upload engine, always has a result to move while the next inputs go up,
+    #  1. the grad-image nodes of the smallest pool first: they need only their own 88 MB of grads, so the download engine
+    #     (which carries more bytes than the upload engine and bounds the step) gets its first 268 MB result after ~2 ms
+    #     and moves it while the P2 map goes up; then that pool's forward nodes (the map is uploaded right before its
+    #     first use), then the larger pool's forward and grad-image nodes.  A two-engine model of the step with this
+    #     box's copy rates (55 / 56 GB/s alone, 47 GB/s each way when both are busy) gives 31.3 ms for "forward first"
+    #     and 28.7 ms for this order,
     #  2. the forward nodes of the empty levels (their maps are still uploaded: they are inputs of the call),
     #  3. the grad-image nodes of the EMPTY levels: their result is the op's zero-fill, which the host-buffer API writes
     #     straight into host memory -- on this thread, while the copies queued above are in flight.
@@ -688,15 +691,24 @@ def run_ours(args):
 
             def dmap(lv):
                 if lv not in d_img:
-                    d_img[lv] = h_images[lv].to(dev, non_blocking=True)
+                    d_img[lv] = rb.upload(h_images[lv])       # on the pipeline's upload stream: uploads keep their issue order
                 return d_img[lv]
-            for crop in sorted(CROPS):
+            def fwd_nodes(crop):
                 for i in order_b1:
                     if ops[i]["crop"] == crop:      # mixed call: device-resident map, host boxes -> host result
                         outs[i] = rb.crop_and_resize_3d(dmap(ops[i]["level"]), h[i]["boxes"], h[i]["bidx"], crop)
+
+            def bwd_nodes(crop):
                 for i in order_b1:
                     if ops[i]["crop"] == crop:
                         outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
+            for j, crop in enumerate(sorted(CROPS)):
+                if j == 0 and len(CROPS) > 1 and os.environ.get("BENCH_E2E_ORDER", "ready-first") != "forward-first":   # smallest input first (see above)
+                    bwd_nodes(crop)
+                    fwd_nodes(crop)
+                else:
+                    fwd_nodes(crop)
+                    bwd_nodes(crop)
             for i in order_b0:
                 outs[i] = rb.crop_and_resize_3d(dmap(ops[i]["level"]), h[i]["boxes"], h[i]["bidx"], ops[i]["crop"])
             for i in order_b0:                          # host-side zero-fill: runs while the copies above are in flight

@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import roi3d_b200 as rb, roi3d_synth
 dev = torch.device("cuda", 0)
 lib = rb._lib.load()
+if os.environ.get("NMS_EXPERIMENT"):
+    rb.set_option("car_experiment", int(os.environ["NMS_EXPERIMENT"]))   # 8: tail masks without the kept-row skip
 cases = [
     ("cfg1 6000->1000 @0.7 (SURVEY 8d boxes)", 6000, 1000, 0.7, dict()),
     ("6000->1000 @0.3", 6000, 1000, 0.3, dict()),

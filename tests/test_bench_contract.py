@@ -34,3 +34,31 @@ def test_reference_arm_other_ranks_exit_quietly():
     rc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, env=env)
     assert rc.returncode == 0 and rc.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_ours_line_has_the_contract_keys(tmp_path):
+    """One short run of the GPU arm: a single JSON line on stdout carrying every key the driver reads."""
+    out = tmp_path / "ours.json"
+    with open(out, "w") as f:
+        rc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-cfg4"],
+                            stdout=f, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert rc.returncode == 0, rc.stderr[-2000:]
+    lines = [ln for ln in out.read_text().splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["unit"] == "ROIs/s" and d["dtype"] == "f32" and d["scaling"] == "weak"
+    assert d["gpu_launches"] > 0 and d["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["secondary"]["nms3d_ms_6k"] > 0 and r["secondary"]["nms3d_kept_6k"] == 1000
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 10 ** 9 and e["d2h_bytes_per_step"] > 10 ** 9
+    assert e["value"] < d["value"]                       # host buffers + PCIe inside the timed region
+    assert d["pyramid_fused"]["ms_per_step"] > 0
