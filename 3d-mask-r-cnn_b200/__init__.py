@@ -31,6 +31,7 @@ from .custom_op import (        # noqa: E402,F401
     deferred,
     synchronize,
     get_option,
+    host_pipeline,
     kernel_launches,
     mask_targets,
     non_max_suppression_3d,

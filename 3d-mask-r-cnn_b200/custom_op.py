@@ -35,7 +35,7 @@ __all__ = [
     "crop_and_resize_3d_grad_boxes", "non_max_suppression_3d", "CropAndResize3DFunction",
     "non_max_suppression_3d_batched", "non_max_suppression_3d_per_class", "non_max_suppression_3d_graph",
     "pyramid_roi_align_3d", "PyramidROIAlign3DFunction", "overlaps_3d", "decode_proposals", "top_k_set", "proposal_layer",
-    "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize", "upload",
+    "set_option", "get_option", "kernel_launches", "reset_kernel_launches", "deferred", "synchronize", "upload", "host_pipeline",
 ]
 
 METHODS = {"trilinear": 0, "nearest": 1}
@@ -81,6 +81,7 @@ class _HostPipe:
         self.d2h = torch.cuda.Stream(device)
         self.pending = []                  # events of D2H copies not yet waited for (deferred mode)
         self.deferred = 0
+        self.held = []                     # (pinned result, device result) pairs whose download waits for the block's end
 
     @classmethod
     def get(cls, device):
@@ -104,8 +105,36 @@ class deferred:
     def __exit__(self, *exc):
         self.pipe.deferred -= 1
         if self.pipe.deferred == 0:
+            pipe = self.pipe
+            if pipe.held:                  # "uploads first" policy: every download of the block starts after its last upload
+                dev = pipe.held[0][1].device
+                pipe.d2h.wait_stream(pipe.h2d)
+                pipe.d2h.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(pipe.d2h):
+                    for res, out in pipe.held:
+                        res.copy_(out, non_blocking=True)
+                        out.record_stream(pipe.d2h)
+                    ev = torch.cuda.Event()
+                    ev.record(pipe.d2h)
+                pipe.pending.append(ev)
+                pipe.held.clear()
             synchronize()
         return False
+
+
+_UPLOADS_FIRST = [False]
+
+
+def host_pipeline(uploads_first=None):
+    """Copy policy of `deferred` blocks.  Default (False): full duplex -- each result is downloaded as soon as its kernel
+    has finished, while later inputs go up; right for one process per host link.  `uploads_first=True`: all downloads of
+    a block start after its last upload -- an experiment for hosts shared by several ranks whose memory system gives more
+    one-directional than duplex bandwidth (this pool's 8-GPU box: 233 GB/s up alone, 128 GB/s down alone, 82 + 82 GB/s
+    duplex, profiles/pcie_probe.py); measured there at 174.0 vs 169.8 ms per 8-rank step, i.e. no gain.  Returns the
+    policy in force."""
+    if uploads_first is not None:
+        _UPLOADS_FIRST[0] = bool(uploads_first)
+    return _UPLOADS_FIRST[0]
 
 
 def synchronize():
@@ -163,6 +192,9 @@ def _finish(out, host, as_numpy):
         res = out.cpu()                                # small and synchronous: one blocking copy
         return res.numpy() if as_numpy else res
     res = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    if pipe.deferred and _UPLOADS_FIRST[0]:
+        pipe.held.append((res, out))
+        return res.numpy() if as_numpy else res
     pipe.d2h.wait_stream(torch.cuda.current_stream(out.device))
     with torch.cuda.stream(pipe.d2h):
         res.copy_(out, non_blocking=True)

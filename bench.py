@@ -715,6 +715,12 @@ def run_ours(args):
                 outs[len(ops) + i] = rb.crop_and_resize_3d_grad_image(h[i]["grads"], h[i]["boxes"], h[i]["bidx"], ops[i]["shape"])
         return outs
 
+    # Copy policy: full duplex (each result goes down as soon as its kernel has finished).  The alternative, every rank
+    # uploading its whole step before any download starts (BENCH_E2E_PIPE=uploads-first), was measured on the 8-GPU box
+    # because its probe shows more one-directional than duplex host bandwidth (233 / 128 vs 82 + 82 GB/s): 174.0 vs
+    # 169.8 ms/step -- no gain, the shared host is the limit either way.
+    pipe_mode = os.environ.get("BENCH_E2E_PIPE", "duplex")
+    rb.host_pipeline(uploads_first=(pipe_mode == "uploads-first"))
     e2e_steps = max(2, min(args.steps, 5))
     if args.no_e2e:
         e2e_steps, e2e_s = 1, float("inf")
@@ -726,6 +732,7 @@ def run_ours(args):
             e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
+    rb.host_pipeline(uploads_first=False)
     e2e_by_rank = rb.sharding.gather_over_ranks(e2e_s)
     e2e_s = rb.sharding.max_over_ranks(e2e_s)
     e2e_value = world * total_rois * e2e_steps / e2e_s
@@ -766,7 +773,7 @@ def run_ours(args):
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3),
-                "ms_per_step_by_rank": [round(v / e2e_steps * 1e3, 2) for v in e2e_by_rank],
+                "ms_per_step_by_rank": [round(v / e2e_steps * 1e3, 2) for v in e2e_by_rank], "copy_policy": pipe_mode,
                 "pcie_gbs_by_rank": [{"h2d": round(h2d * e2e_steps / v / 1e9, 1), "d2h": round(d2h * e2e_steps / v / 1e9, 1)}
                                      for v in e2e_by_rank] if not args.no_e2e else None,
                 "note": "host buffers in / host results out; both copy directions run concurrently, so each rate is bytes of that "

@@ -306,6 +306,30 @@ def test_car_empty_and_single(rb, cuda_device):
     assert isinstance(hz, np.ndarray) and hz.shape == (2, 4, 4, 4, 8) and hz.dtype == np.float32 and not hz.any()
 
 
+@pytest.mark.parametrize("uploads_first", [False, True])
+def test_host_buffer_pipeline_policies(rb, cuda_device, uploads_first):
+    """Host buffers in, host results out, several independent ops inside one `deferred` block: both copy policies
+    (full duplex / uploads first) return the oracle's results once the block has exited."""
+    B, H, W, D, C, n, crop = 2, 8, 8, 16, 256, 12, (14, 14, 14)
+    image, boxes, bidx, grads = car_inputs(4242, B, H, W, D, C, n, crop)
+    big = np.tile(image, (1, 4, 4, 2, 1))                       # > 1 MiB: goes through the upload stream
+    try:
+        rb.host_pipeline(uploads_first=uploads_first)
+        with rb.deferred():
+            d_img = rb.upload(big)
+            outs = [rb.crop_and_resize_3d(d_img, boxes, bidx, crop) for _ in range(2)]
+            gis = [rb.crop_and_resize_3d_grad_image(grads, boxes, bidx, big.shape) for _ in range(2)]
+    finally:
+        rb.host_pipeline(uploads_first=False)
+    ref = oracle.crop_and_resize_3d(big, boxes, bidx, crop)
+    gref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, big.shape)
+    to_np = lambda t: t if isinstance(t, np.ndarray) else t.numpy()      # noqa: E731  (host results: numpy or pinned CPU tensors)
+    for o in outs:
+        assert not getattr(o, "is_cuda", False) and np.array_equal(to_np(o), ref)
+    for g in gis:
+        assert not getattr(g, "is_cuda", False) and rel_ok(to_np(g), gref, BWD_TOL)
+
+
 @pytest.mark.parametrize("case", [CAR_CASES[0], CAR_CASES[1], CAR_CASES[7]])
 def test_car_box_index_out_of_range_is_guarded(rb, cuda_device, case):
     """The reference reads out of bounds for a box_index outside [0, B) (no check in CAR.so / GI.so / GB.so).  Here
