@@ -157,6 +157,11 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
     // has enough outputs to amortise its per-CTA tables -- from 10 x 10 at any channel count >= 32, from 7 x 7 when
     // the channel chunks are full (C >= 128); below that the direct gather wins or ties
     if (variant == 0) variant = (plane_ok && ((C >= 32 && ph * pw >= 100) || (C >= 128 && ph * pw >= 49))) ? 2 : 1;
+    if (variant == 5 && plane_ok) {                                     // plane kernel fed by TMA gather4 row copies
+        const int rc = launch_car3d_fwd_plane_g4(image, boxes, box_index, g, extrapolation_value, crops, s);
+        if (rc != ROI3D_EUNSUPPORTED) return rc;
+        variant = 2;
+    }
     if (variant == 4 && plane_ok) {                                     // row-walk separable kernel
         const int rc = launch_car3d_fwd_sep(image, boxes, box_index, g, extrapolation_value, crops, nullptr, false, s);
         if (rc != ROI3D_EUNSUPPORTED) return rc;

@@ -27,6 +27,7 @@
 // and issues two vector REDs (floor z, ceil z) instead of 8 per grads element.
 #include "roi3d_common.cuh"
 #include "roi3d_car_pyr.cuh"
+#include <cuda.h>                            // CUtensorMap (the encode function is fetched from the driver at run time)
 #include <type_traits>
 #include <math.h>
 #include <string.h>
@@ -533,6 +534,168 @@ car3d_fwd_plane_tma_kernel(const float *__restrict__ image, const float *__restr
 }
 
 // ---------------------------------------------------------------------------------
+// forward, fed by the Blackwell TMA row gather (variant 5).  Same structure as variant 3, but stage A's gather is
+// cp.async.bulk.tensor.2d ... tile::gather4 (SASS UTMALDG with the gather4 modifier) on a 2-D tensor map
+// [B*H*W*D rows, C columns] with a box of one channel chunk x 1 row: ONE instruction brings the chunk rows of FOUR
+// footprint voxels (4 x 256 B), so a depth sample of ~81 voxels x 2 taps takes 42 copies instead of 162 -- the
+// granularity problem of variant 3 (profiles/README.md).  voff[] holds row indices here, not element offsets.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_gather4(unsigned dst, const CUtensorMap *map, int col, int r0, int r1, int r2, int r3, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(mbar) : "memory");
+}
+
+// wait with a bound: a transaction-count mismatch (the only way this can block) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(unsigned mbar, unsigned parity) {
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+__global__ void __launch_bounds__(PL_THREADS, 3)
+car3d_fwd_plane_g4_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ boxes,
+                          const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
+                          float *__restrict__ crops)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off = 0;
+    PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
+    OutEntry *otab = reinterpret_cast<OutEntry *>(smem_raw + off); off += sizeof(OutEntry) * (size_t)L.otab;
+    int *vrow = reinterpret_cast<int *>(smem_raw + off); off += (sizeof(int) * (size_t)L.zcap + 15) & ~size_t(15);
+    off += (128u - ((smem_u32(smem_raw) + (unsigned)off) & 127u)) & 127u;     // tensor copies need 128-byte aligned destinations
+    const unsigned ebytes = (unsigned)L.cl * 16;
+    unsigned char *Rf = smem_raw + off; off += (size_t)L.zcap * ebytes;      // raw floor-z taps
+    unsigned char *Rc = smem_raw + off; off += (size_t)L.zcap * ebytes;      // raw ceil-z taps
+    unsigned char *Zraw = smem_raw + off; off += (size_t)L.zcap * ebytes;    // z-lerped plane
+    __shared__ __align__(8) unsigned long long s_mbar;
+
+    int bid = blockIdx.x;
+    const int chunk = bid % L.chunks; bid /= L.chunks;
+    const int ks = bid % L.ksplits;
+    const int b = bid / L.ksplits;
+    if (threadIdx.x < 6) S.box[threadIdx.x] = __ldg(boxes + (size_t)b * 6 + threadIdx.x);
+    __syncthreads();
+    const unsigned mbar = smem_u32(&s_mbar);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    build_axis_tables(S, g);
+    build_y_tiles(S, g, L.zcap);
+
+    const AxisTab &Y = S.ax[0], &X = S.ax[1];
+    const int nx = X.n;
+    const int cl = L.cl;
+    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
+    const int c4 = chunk * cl + lane;
+    const bool on = c4 < g.C / 4;
+    const int bimg = __ldg(box_index + b);
+    const bool bad_img = (unsigned)bimg >= (unsigned)g.B;
+    float *crop = crops + (long long)b * g.ph * g.pw * g.pd * g.C + c4 * 4;
+    const float4 ext4 = make_float4(ext, ext, ext, ext);
+    const float z1 = S.box[2], z2 = S.box[5];
+    const float zscale = axis_scale(z1, z2, g.D, g.pd);
+    const int kper = (g.pd + L.ksplits - 1) / L.ksplits;
+    const int k0 = min(ks * kper, g.pd), k1 = min(g.pd, k0 + kper);
+    const unsigned rf_u32 = smem_u32(Rf), rc_u32 = smem_u32(Rc);
+    const unsigned z_u32 = smem_u32(Zraw) + lane * 16;
+    const unsigned otab_u32 = smem_u32(otab);
+    const long long ostride = (long long)vs * g.pd * g.C;
+    const int col0 = chunk * cl * 4;                              // first channel of this chunk (tensor-map column)
+    unsigned parity = 0;
+
+    for (int tl = 0; tl < S.ntiles; ++tl) {
+        const int ya = S.tile_y0[tl], yb = S.tile_y0[tl + 1];
+        const int r0 = S.tile_r0[tl], r1 = S.tile_r1[tl];
+        const int nvox = (r1 >= r0) ? (r1 - r0 + 1) * nx : 0;
+        const int nout = (yb - ya) * g.pw;
+        for (int idx = threadIdx.x; idx < nvox; idx += PL_THREADS) {
+            const int r = idx / nx, cx = idx - r * nx;
+            vrow[idx] = ((bimg * g.H + Y.list[r0 + r]) * g.W + X.list[cx]) * g.D;      // tensor-map row of (y, x, z = 0)
+        }
+        for (int idx = threadIdx.x; idx < nout; idx += PL_THREADS) {
+            const int yy = idx / g.pw, x = idx - yy * g.pw, y = ya + yy;
+            const int py0 = Y.pos0[y], px0 = X.pos0[x];
+            OutEntry e;
+            if (py0 < 0 || px0 < 0) {
+                e.o_top = 0xFFFFFFFFu; e.o_bot = 0xFFFFFFFFu; e.xl = 0.f; e.yl = 0.f;
+            } else {
+                const unsigned rt_ = (unsigned)(py0 - r0) * nx, rb = (unsigned)(Y.pos1[y] - r0) * nx;
+                const unsigned px1 = (unsigned)X.pos1[x];
+                e.o_top = ((rt_ + px0) * ebytes) | (((rt_ + px1) * ebytes) << 16);
+                e.o_bot = ((rb + px0) * ebytes) | (((rb + px1) * ebytes) << 16);
+                e.xl = X.t[x]; e.yl = Y.t[y];
+            }
+            otab[idx] = e;
+        }
+        __syncthreads();                                       // tables (and the mbarrier init) visible
+
+        // warp 0 gathers depth sample k into the raw buffers: one gather4 per four voxels and tap
+        auto issue = [&](int k) {
+            if (threadIdx.x < 64) {                            // warp 0: floor taps, warp 1: ceil taps
+                const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
+                const int tap = threadIdx.x >> 5, ln = threadIdx.x & 31;
+                const int zt = tap ? (int)ceilf(in_z) : (int)floorf(in_z);
+                const unsigned dst = tap ? rc_u32 : rf_u32;
+                const int ngroups = (nvox + 3) >> 2;
+                fence_proxy_async();                           // earlier generic reads of the raw buffers are done
+                // the phase cannot complete before this arrival, whatever the order of the copies' complete_tx
+                if (threadIdx.x == 0) mbar_expect_tx(mbar, 2u * (unsigned)ngroups * 4u * ebytes);
+                for (int gq = ln; gq < ngroups; gq += 32) {
+                    const int i0 = gq * 4, last = nvox - 1;
+                    const int ra = vrow[i0], rb_ = vrow[min(i0 + 1, last)], rc_ = vrow[min(i0 + 2, last)], rd = vrow[min(i0 + 3, last)];
+                    tma_gather4(dst + (unsigned)i0 * ebytes, &tmap, col0, ra + zt, rb_ + zt, rc_ + zt, rd + zt, mbar);
+                }
+            }
+        };
+        auto zvalid = [&](int k) { return k < k1 && nvox > 0 && !bad_img && !axis_invalid(axis_coord(z1, z2, g.D, g.pd, k, zscale), g.D); };
+
+        int kfirst = k0;
+        while (kfirst < k1 && !zvalid(kfirst)) ++kfirst;
+        if (kfirst < k1) issue(kfirst);
+
+        for (int k = k0; k < k1; ++k) {
+            float *o = crop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
+            if (!zvalid(k)) {
+                if (on)
+                    for (int idx = slot; idx < nout; idx += vs, o += ostride) st_stream4(o, ext4);
+                continue;
+            }
+            const float in_z = axis_coord(z1, z2, g.D, g.pd, k, zscale);
+            const float zl = __fsub_rn(in_z, floorf(in_z));
+            mbar_wait_bounded(mbar, parity);                           // the taps of sample k have landed
+            parity ^= 1u;
+            if (on) {
+                for (int idx = slot; idx < nvox; idx += vs) {
+                    const float4 f = lds128(rf_u32 + idx * ebytes + lane * 16);
+                    const float4 c = lds128(rc_u32 + idx * ebytes + lane * 16);
+                    sts128(z_u32 + idx * ebytes, lerp_rn(f, c, zl));
+                }
+            }
+            __syncthreads();                                   // plane complete, raw buffers free
+            int kn = k + 1;
+            while (kn < k1 && !zvalid(kn)) ++kn;
+            if (kn < k1) issue(kn);                            // flies during stage B
+            if (on) {
+#pragma unroll 2
+                for (int idx = slot; idx < nout; idx += vs, o += ostride) {
+                    const uint4 e = lds128u(otab_u32 + idx * 16);
+                    const bool bad = e.x == 0xFFFFFFFFu;
+                    const unsigned et = bad ? 0u : e.x, eb = bad ? 0u : e.y;
+                    const float xl = __uint_as_float(e.z), yl = __uint_as_float(e.w);
+                    const float4 tlv = lds128(z_u32 + (et & 0xFFFFu)), trv = lds128(z_u32 + (et >> 16));
+                    const float4 blv = lds128(z_u32 + (eb & 0xFFFFu)), brv = lds128(z_u32 + (eb >> 16));
+                    const float4 top = lerp_rn(tlv, trv, xl), bot = lerp_rn(blv, brv, xl);
+                    st_stream4(o, sel4(bad, ext4, lerp_rn(top, bot, yl)));
+                }
+            }
+            __syncthreads();                                   // plane free for the next sample
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // backward (grad image).  grad_image must be zero-filled before the launch.
 // ---------------------------------------------------------------------------------
 struct __align__(8) Contrib { unsigned off; float w; };   // staged-slice byte offset of a sample, its weight
@@ -834,6 +997,64 @@ int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
     kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, PyrParams{});
+    ROI3D_LAUNCH_CHECK();
+    return ROI3D_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn plane_encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int launch_car3d_fwd_plane_g4(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                              float ext, float *crops, cudaStream_t stream)
+{
+    PlaneLaunch L;
+    L.cl = 16;
+    while (L.cl > 1 && L.cl / 2 >= g.C / 4) L.cl /= 2;
+    const long long rows = (long long)g.B * g.H * g.W * g.D;
+    // a gather4 lands four chunk rows at once: 4 * cl * 16 bytes must keep the 128-byte alignment of tensor-copy destinations
+    if (L.cl < 2 || rows >= (1ll << 31) || (reinterpret_cast<uintptr_t>(image) & 15) || (g.C * 4) % 16) return ROI3D_EUNSUPPORTED;
+    const int nxmax = min(2 * g.pw, g.W);
+    L.otab = min(g.ph * g.pw, max(PL_MAXOUT, g.pw));
+    const size_t eb = (size_t)L.cl * 16;
+    L.zcap = (int)max((size_t)2 * nxmax, (size_t)(22 * 1024) / eb);       // 3 buffers of ~22 KB
+    L.zcap = (L.zcap + 3) & ~3;                                            // whole gather4 groups
+    if ((size_t)L.zcap * eb > 65535) return ROI3D_EUNSUPPORTED;
+    const size_t smem = a16(sizeof(PlaneShared)) + sizeof(OutEntry) * (size_t)L.otab + a16(sizeof(int) * (size_t)L.zcap) +
+                        256 + 3 * (size_t)L.zcap * eb;
+    if (smem > 200 * 1024) return ROI3D_EUNSUPPORTED;
+    L.chunks = (g.C / 4 + L.cl - 1) / L.cl;
+    L.ksplits = pick_ksplits(g, L.chunks);
+    EncodeTiledFn encode = plane_encode_tiled_fn();
+    if (!encode) return ROI3D_EUNSUPPORTED;
+    // image [B, H, W, D, C] viewed as a 2-D tensor (C columns, B*H*W*D rows); box = one channel chunk x 1 row (gather4
+    // brings four such rows per instruction)
+    CUtensorMap tmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)g.C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.C * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)L.cl * 4, 1}, estr[2] = {1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(image), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return ROI3D_EUNSUPPORTED;
+    auto kern = car3d_fwd_plane_g4_kernel;
+    if (smem > 48 * 1024)
+        ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
+    const long long grid = (long long)g.n * L.ksplits * L.chunks;
+    if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
+    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(tmap, boxes, box_index, g, L, ext, crops);
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }

@@ -179,6 +179,8 @@ int launch_car3d_grad_boxes(const float *grads, const float *image, const float 
                             const CarGeom &g, float *grad_boxes, cudaStream_t stream);
 int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                                float ext, float *crops, cudaStream_t stream);
+int launch_car3d_fwd_plane_g4(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
+                              float ext, float *crops, cudaStream_t stream);
 int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,

@@ -183,7 +183,7 @@ CAR_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])               # direct, plane-staged, plane-staged fed by TMA bulk copies, row-walk
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])            # direct, plane-staged, fed by TMA bulk copies, row-walk, fed by TMA gather4
 @pytest.mark.parametrize("case", CAR_CASES)
 def test_car_forward_matches_oracle(rb, cuda_device, case, variant):
     B, H, W, D, C, n, crop = case
@@ -266,7 +266,7 @@ def test_car_fuzz_all_variants(rb, cuda_device, seed):
     ref = oracle.crop_and_resize_3d(image, boxes, bidx, crop, "trilinear", ext)
     gref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape)
     t = [dev(x, cuda_device) for x in (image, boxes, bidx, grads)]
-    for fv in (0, 1, 2, 3, 4):
+    for fv in (0, 1, 2, 3, 4, 5):
         rb.custom_op.set_option("car_fwd_variant", fv)
         out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=ext).cpu().numpy()
         assert np.array_equal(out, ref), ("forward variant", fv, image.shape, crop)
@@ -342,7 +342,7 @@ def test_car_box_index_out_of_range_is_guarded(rb, cuda_device, case):
     bidx_bad[bad] = [-1, B, 2 ** 30]
     good = ~bad
     t = [dev(x, cuda_device) for x in (image, boxes, bidx_bad, grads)]
-    for fv in (1, 2, 3, 4):
+    for fv in (1, 2, 3, 4, 5):
         rb.custom_op.set_option("car_fwd_variant", fv)
         out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=7.0).cpu().numpy()
         assert np.array_equal(out[good], oracle.crop_and_resize_3d(image, boxes[good], bidx[good], crop, "trilinear", 7.0))
