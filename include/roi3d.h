@@ -255,8 +255,9 @@ ROI3D_API int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y
  * roi3d_set_option: knobs of the CALLING THREAD (thread-local; another thread's calls are unaffected), used by the
  * benchmarks and tests to select a kernel variant; the defaults (0) are the production choice.
  *   "car_fwd_variant"   0 = auto, 1 = direct gather, 2 = plane-staged separable, 3 = plane-staged fed by TMA bulk
- *                       copies, 4 = row-walk separable (z / x / y lerps each evaluated once); 3 and 4 are bit-exact
- *                       but slower at the row sizes of this path: opt-in
+ *                       copies, 4 = row-walk separable (z / x / y lerps each evaluated once), 5 = plane-staged fed by
+ *                       TMA gather4 row copies (cp.async.bulk.tensor.2d ... tile::gather4); 3-5 are bit-exact; 3 and 4
+ *                       are slower, 5 is level with 2 at 14^3 and slower at 7^3: opt-in
  *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged RED scatter, 3 = output-stationary (every
  *                       voxel stored once, no zero-fill, no atomics, deterministic; slower: opt-in)
  *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane / row-walk kernels
