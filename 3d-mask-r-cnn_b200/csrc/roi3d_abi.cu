@@ -192,12 +192,16 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     const bool plane_ok = method == ROI3D_METHOD_TRILINEAR && C % 4 == 0 && ph <= 64 && pw <= 64 && pd <= 64 && aligned;
     const bool os_ok = method == ROI3D_METHOD_TRILINEAR && aligned && car3d_grad_image_os_supported(g);
     const bool have_in = n > 0 && grads && boxes && box_ind;
-    // auto: the plane-staged RED scatter.  The output-stationary kernel (variant 3: every voxel stored once, no
-    // zero-fill, no atomics, deterministic; DRAM traffic 1.03 vs 1.80 GB at cfg2 14^3) is opt-in: it is latency-bound on
-    // per-(box, tile) bookkeeping and measures 0.55-0.64 ms against 0.39 ms (profiles/r2_os_grad_image_ncu.txt)
-    if (variant == 0) variant = (plane_ok && C >= 32) ? 2 : 1;
+    // auto: the plane-staged RED scatter with its grads slices staged by TMA tensor tile copies (variant 4; cfg2 14^3:
+    // 0.318 vs 0.371 ms with per-thread loads, profiles/bwd_tma_sweep.py); variant 2 keeps the LDG staging.  The
+    // output-stationary kernel (variant 3: every voxel stored once, no zero-fill, no atomics, deterministic; DRAM traffic
+    // 1.03 vs 1.74 GB at cfg2 14^3) is opt-in: it is latency-bound on per-(box, tile) bookkeeping and measures
+    // 0.55-0.64 ms (profiles/r2_os_grad_image_ncu.txt)
+    if (variant == 0) variant = (plane_ok && C >= 32) ? 4 : 1;
     if (variant == 3 && os_ok && have_in) return launch_car3d_grad_image_os(grads, boxes, box_ind, g, grad_image, s);
     if (variant == 3) variant = (plane_ok && C >= 32) ? 2 : 1;
+    bool tma = variant == 4 && plane_ok;
+    if (variant == 4) variant = plane_ok ? 2 : 1;
     const bool plane = have_in && variant == 2 && plane_ok;
     // plane path: the zero-fill is a kernel that the scatter kernel overlaps with (programmatic dependent launch;
     // option "pdl" = 1 restores memset + plain stream order)
@@ -205,6 +209,10 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     if (!fused_fill) ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
     if (n == 0) return ROI3D_OK;
     if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;
+    if (plane && tma) {
+        const int rc = launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill, true);
+        if (rc != ROI3D_EUNSUPPORTED) return rc;        // (nothing has been launched when the TMA build declines a shape)
+    }
     if (plane) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill);
     return launch_car3d_grad_image_direct(grads, boxes, box_ind, g, method, grad_image, s);
 }

@@ -547,7 +547,8 @@ __device__ __forceinline__ void tma_gather4(unsigned dst, const CUtensorMap *map
 
 // wait with a bound: a transaction-count mismatch (the only way this can block) traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(unsigned mbar, unsigned parity) {
-    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+#pragma unroll 1
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {     // try_wait suspends the thread in hardware for a while: not a hot spin
         unsigned ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
@@ -695,6 +696,16 @@ car3d_fwd_plane_g4_kernel(const __grid_constant__ CUtensorMap tmap, const float 
     }
 }
 
+// 3-D tensor tile copy / L2 prefetch (grads viewed as [N*ph*pw rows, pd, C]): the backward's k-slice staging in ONE copy
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 :: "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // ---------------------------------------------------------------------------------
 // backward (grad image).  grad_image must be zero-filled before the launch.
 // ---------------------------------------------------------------------------------
@@ -737,18 +748,27 @@ __device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, c
     __syncthreads();
 }
 
-template <int V, bool PYR, bool FULL = false>
+// TMA: the k-slice of grads is staged by ONE tensor tile copy (cp.async.bulk.tensor.3d, box = channel chunk x 1 depth
+// sample x zcap (y, x) samples) issued by one thread and awaited on an mbarrier, instead of 2-3 dependent batches of
+// per-thread loads + shared stores; the next slice is pulled towards L2 by one tensor prefetch instruction.
+template <int V, bool PYR, bool FULL = false, bool TMA = false>
 __global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
-                              float *__restrict__ grad_image, const PyrParams P, const int only_image)
+                              float *__restrict__ grad_image, const PyrParams P, const int only_image,
+                              const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int UNR = (V == 1) ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off = 0;
     PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);  off += (sizeof(PlaneShared) + 15) & ~size_t(15);
     BwdLists &B = *reinterpret_cast<BwdLists *>(smem_raw + off);  off += (sizeof(BwdLists) + 15) & ~size_t(15);
+    if constexpr (TMA) off += (128u - ((smem_u32(smem_raw) + (unsigned)off) & 127u)) & 127u;   // tensor copies: 128-byte aligned destination
     unsigned char *Graw = smem_raw + off;                          // staged grads slice [(y-ya)*pw + x][V][cl] float4
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const unsigned mbar = smem_u32(&s_mbar);
+    if constexpr (TMA) { if (threadIdx.x == 0) mbar_init(mbar, 1); }                            // visible after the prologue's barriers
+    unsigned tma_parity = 0;
 
     int bid = blockIdx.x;
     const int chunk = bid % L.chunks; bid /= L.chunks;
@@ -825,7 +845,16 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
             const long long zf = (long long)(int)zfl * g.C, zc = (long long)(int)ceilf(in_z) * g.C;
             const float zl = __fsub_rn(in_z, zfl), wzf = __fsub_rn(1.0f, zl);
             // ---- stage A': stage the k-slice of grads (each element read once) -------------
-            {
+            if constexpr (TMA) {
+                if (threadIdx.x == 0) {
+                    fence_proxy_async();                       // the previous slice's generic reads (before the barrier) are done
+                    mbar_expect_tx(mbar, (unsigned)L.zcap * ebytes);
+                    tma_load_3d(smem_u32(Graw), &tmap, chunk * cl * V * 4, k, (b * g.ph + ya) * g.pw, mbar);
+                    if (k + 1 < k1) tma_prefetch_3d(&tmap, chunk * cl * V * 4, k + 1, (b * g.ph + ya) * g.pw);
+                }
+                mbar_wait_bounded(mbar, tma_parity);           // every thread sees the landed slice
+                tma_parity ^= 1u;
+            } else {
                 const float *gp = gcrop + (((long long)ya * g.pw + slot) * g.pd + k) * g.C;
                 for (int base = slot; base < nent; base += vs * UNR, gp += UNR * gstride) {
                     float4 val[UNR][V];
@@ -847,9 +876,9 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
                     }
                 }
             }
-            __syncthreads();
+            if constexpr (!TMA) __syncthreads();
             // ---- L2 prefetch of the next depth sample's grads slice ----------------------------
-            if (k + 1 < k1 && (lane & 7) == 0) {
+            if (!TMA && k + 1 < k1 && (lane & 7) == 0) {
                 const float *gn = gcrop + (((long long)ya * g.pw + slot) * g.pd + (k + 1)) * g.C;
                 for (int idx = slot; idx < nent; idx += vs, gn += gstride) {
 #pragma unroll
@@ -1101,7 +1130,7 @@ static inline unsigned fill_grid() {
 
 static int launch_grad_plane_impl(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
                                   float *grad_image, const PyrParams *pyr, cudaStream_t stream, bool zero_fill = false,
-                                  bool pdl_after_fill = false)
+                                  bool pdl_after_fill = false, bool tma = false)
 {
     PlaneLaunch L;
     int V;
@@ -1119,18 +1148,39 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
             const int ty = max(1, L.zcap / g.pw), nt = (g.ph + ty - 1) / ty;
             L.zcap = ((g.ph + nt - 1) / nt) * g.pw;
         }
-        smem = fixed + (size_t)L.zcap * eb;
+        smem = fixed + (size_t)L.zcap * eb + (tma ? 128 : 0);
         if (smem <= 200 * 1024) break;
         if (V > 1) V = 1; else if (L.cl > 1) L.cl /= 2; else return ROI3D_EUNSUPPORTED;
     }
     L.chunks = (g.C / 4 + L.cl * V - 1) / (L.cl * V);
     L.ksplits = pick_ksplits(g, L.chunks);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (tma) {
+        // grads [N, ph, pw, pd, C] viewed as a 3-D tensor (C, pd, N*ph*pw); box = one channel chunk x 1 depth sample x zcap rows
+        const long long rows = (long long)g.n * g.ph * g.pw;
+        EncodeTiledFn encode = plane_encode_tiled_fn();
+        if (!encode || L.zcap > 256 || L.cl * V * 4 > 256 || rows >= (1ll << 31) ||
+            (reinterpret_cast<uintptr_t>(grads) & 15) || (g.C * 4) % 16)
+            return ROI3D_EUNSUPPORTED;
+        const cuuint64_t dims[3] = {(cuuint64_t)g.C, (cuuint64_t)g.pd, (cuuint64_t)rows};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.C * 4, (cuuint64_t)g.pd * g.C * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(L.cl * V * 4), 1, (cuuint32_t)L.zcap}, estr[3] = {1, 1, 1};
+        if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(grads), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ROI3D_EUNSUPPORTED;
+    }
     // FULL pays off in the pyramid instantiation only (cfg2 14^3: 0.377 vs 0.398 ms); in the plain one ptxas then spills
     // inside the gather loop (0.398 vs 0.371 ms) -- measured with profiles/full_ab.py (car_experiment bit 2 flips the choice)
-    const bool full = (g.C / 4) % (L.cl * V) == 0 && ((pyr != nullptr) != ((option_value(OPT_EXPERIMENT) & 2) != 0));
-    using K = void (*)(const float *, const float *, const int *, CarGeom, PlaneLaunch, float *, const PyrParams, const int);
+    const bool full = (g.C / 4) % (L.cl * V) == 0 && ((pyr != nullptr || tma) != ((option_value(OPT_EXPERIMENT) & 2) != 0));
+    using K = void (*)(const float *, const float *, const int *, CarGeom, PlaneLaunch, float *, const PyrParams, const int, const CUtensorMap);
     K kern;
-    if (V == 2) kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<2, true, true> : (K)car3d_grad_image_plane_kernel<2, true, false>)
+    if (tma && pyr) kern = (V == 2) ? (full ? (K)car3d_grad_image_plane_kernel<2, true, true, true> : (K)car3d_grad_image_plane_kernel<2, true, false, true>)
+                                    : (full ? (K)car3d_grad_image_plane_kernel<1, true, true, true> : (K)car3d_grad_image_plane_kernel<1, true, false, true>);
+    else if (tma)   kern = (V == 2) ? (full ? (K)car3d_grad_image_plane_kernel<2, false, true, true> : (K)car3d_grad_image_plane_kernel<2, false, false, true>)
+                                    : (full ? (K)car3d_grad_image_plane_kernel<1, false, true, true> : (K)car3d_grad_image_plane_kernel<1, false, false, true>);
+    else if (V == 2) kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<2, true, true> : (K)car3d_grad_image_plane_kernel<2, true, false>)
                            : (full ? (K)car3d_grad_image_plane_kernel<2, false, true> : (K)car3d_grad_image_plane_kernel<2, false, false>);
     else        kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<1, true, true> : (K)car3d_grad_image_plane_kernel<1, true, false>)
                            : (full ? (K)car3d_grad_image_plane_kernel<1, false, true> : (K)car3d_grad_image_plane_kernel<1, false, false>);
@@ -1150,14 +1200,14 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
             zero_fill_kernel<<<fill_grid(), 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
             ROI3D_LAUNCH_CHECK();
             ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
-                                            grad_image, PyrParams{}, split ? img : -1));
+                                            grad_image, PyrParams{}, split ? img : -1, tmap));
             if (img + 1 < (split ? g.B : 1)) ROI3D_LAUNCH_CHECK();
         }
     } else if (pdl_after_fill) {                               // the caller has just enqueued the zero-fill kernel
         ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
-                                        grad_image, pyr ? *pyr : PyrParams{}, -1));
+                                        grad_image, pyr ? *pyr : PyrParams{}, -1, tmap));
     } else {
-        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, -1);
+        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, -1, tmap);
     }
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
@@ -1165,9 +1215,9 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
 
 // zero_fill: the launcher also performs the op's zero-fill of grad_image (as a kernel the scatter kernel overlaps with)
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream, bool zero_fill)
+                                  float *grad_image, cudaStream_t stream, bool zero_fill, bool tma)
 {
-    return launch_grad_plane_impl(grads, boxes, box_ind, g, grad_image, nullptr, stream, zero_fill);
+    return launch_grad_plane_impl(grads, boxes, box_ind, g, grad_image, nullptr, stream, zero_fill, false, tma);
 }
 
 // ---- fused PyramidROIAlign entry points (geometry g: B, C, n = B * R, crop; H/W/D = the largest level, for sizing) ----
@@ -1206,6 +1256,10 @@ int launch_pyramid_grad(const float *grads, float *const grad_images[4], const i
     zero_fill4_kernel<<<fill_grid(), 256, 0, stream>>>(f);
     ROI3D_LAUNCH_CHECK();
     if (g.n == 0) return ROI3D_OK;
+    if (option_value(OPT_CAR_BWD_VARIANT) != 2) {               // TMA-staged grads slices (default); car_bwd_variant 2 = LDG staging
+        const int rc = launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream, false, option_value(OPT_PDL) == 0, true);
+        if (rc != ROI3D_EUNSUPPORTED) return rc;
+    }
     return launch_grad_plane_impl(grads, boxes, nullptr, g, nullptr, &P, stream, false, option_value(OPT_PDL) == 0);
 }
 

@@ -184,7 +184,7 @@ int launch_car3d_fwd_plane_g4(const float *image, const float *boxes, const int 
 int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                            float ext, float *crops, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream, bool zero_fill = false);
+                                  float *grad_image, cudaStream_t stream, bool zero_fill = false, bool tma = false);
 struct PyrParams;
 int launch_car3d_fwd_sep(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                          float ext, void *crops, const PyrParams *pyr, bool half_out, cudaStream_t stream);

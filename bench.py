@@ -436,7 +436,13 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src,
                 "ms": dom["ms"], "ms_p10": dom["ms_p10"], "ms_p50": dom["ms_p50"], "ms_p90": dom["ms_p90"], "reps": reps,
                 "note": "achieved = algorithmic bytes (SURVEY.md 8d) / mean CUDA-event duration of the C-ABI call"
-                        + (" (zero-fill memset + scatter kernel)" if dom["op"].endswith("grad_image") else "")}
+                        + (" (zero-fill kernel + scatter kernel); the 8d formula charges the footprint of every ROI as a DRAM "
+                           "read-modify-write, but overlapping footprints and the tail of the zero-fill are served by the 126 MB "
+                           "L2, so frac can exceed 1: achieved_dram / frac_dram divide the DRAM bytes ncu measured for this call "
+                           "(traffic) by the same time" if dom["op"].endswith("grad_image") else "")}
+    if traffic:
+        roofline["achieved_dram"] = round(traffic / (dom["ms"] * 1e-3) / 1e9, 1)
+        roofline["frac_dram"] = round(roofline["achieved_dram"] / peak, 4)
     sum_bytes = sum(r["alg_bytes"] for r in per_op)
     step_gbs = sum_bytes / (ms_step * 1e-3) / 1e9
 

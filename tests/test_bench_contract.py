@@ -56,7 +56,10 @@ def test_ours_line_has_the_contract_keys(tmp_path):
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["unit"] == "ROIs/s" and d["dtype"] == "f32" and d["scaling"] == "weak"
     assert d["gpu_launches"] > 0 and d["value"] > 0
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    # frac is algorithmic bytes (SURVEY 8d formula) / time / measured peak: the formula charges every footprint as DRAM
+    # traffic, so an L2-friendly scatter can exceed 1; the DRAM bytes ncu measured give frac_dram, which cannot
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] <= 1.25 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["traffic"] > 0 and 0 < r["frac_dram"] <= 1.0
     assert r["secondary"]["nms3d_ms_6k"] > 0 and r["secondary"]["nms3d_kept_6k"] == 1000
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 10 ** 9 and e["d2h_bytes_per_step"] > 10 ** 9

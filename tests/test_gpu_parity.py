@@ -206,7 +206,7 @@ def test_car_forward_nearest(rb, cuda_device, case):
     assert np.array_equal(out, oracle.crop_and_resize_3d(image, boxes, bidx, crop, "nearest", -1.0))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])                  # direct scatter, plane-staged scatter, output-stationary
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])               # direct scatter, plane-staged scatter, output-stationary, TMA-staged scatter
 @pytest.mark.parametrize("case", CAR_CASES)
 def test_car_grad_image_matches_oracle(rb, cuda_device, case, variant):
     B, H, W, D, C, n, crop = case
@@ -270,7 +270,7 @@ def test_car_fuzz_all_variants(rb, cuda_device, seed):
         rb.custom_op.set_option("car_fwd_variant", fv)
         out = rb.crop_and_resize_3d(t[0], t[1], t[2], crop, extrapolation_value=ext).cpu().numpy()
         assert np.array_equal(out, ref), ("forward variant", fv, image.shape, crop)
-    for bv in (0, 1, 2, 3):
+    for bv in (0, 1, 2, 3, 4):
         rb.custom_op.set_option("car_bwd_variant", bv)
         gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
         assert rel_ok(gi, gref, BWD_TOL), ("backward variant", bv, image.shape, crop)
@@ -348,7 +348,7 @@ def test_car_box_index_out_of_range_is_guarded(rb, cuda_device, case):
         assert np.array_equal(out[good], oracle.crop_and_resize_3d(image, boxes[good], bidx[good], crop, "trilinear", 7.0))
         assert np.all(out[bad] == 7.0)
     ref = oracle.crop_and_resize_3d_grad_image(grads[good], boxes[good], bidx[good], image.shape)
-    for bv in (1, 2, 3):
+    for bv in (1, 2, 3, 4):
         rb.custom_op.set_option("car_bwd_variant", bv)
         gi = rb.crop_and_resize_3d_grad_image(t[3], t[1], t[2], image.shape).cpu().numpy()
         assert rel_ok(gi, ref, BWD_TOL)
@@ -447,7 +447,7 @@ def _full_size_backward_vs_oracle(rb, cuda_device, batch, rois_per_image, crops,
             grads = roi3d_synth.grads_like((n,) + crop + (shape[4],), 4000 + level * 10 + crop[0])
             ref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, shape, threads=nt)
             tg = dev(grads, cuda_device)
-            for variant in (0, 2, 3):
+            for variant in (0, 2, 3, 4):
                 rb.custom_op.set_option("car_bwd_variant", variant)
                 gi = rb.crop_and_resize_3d_grad_image(tg, tb, ti, shape).cpu().numpy()
                 assert rel_ok(gi, ref, BWD_TOL), (level, crop, variant)
