@@ -258,8 +258,10 @@ ROI3D_API int roi3d_unpack_bits(const unsigned char *bits, long long n, float *y
  *                       copies, 4 = row-walk separable (z / x / y lerps each evaluated once), 5 = plane-staged fed by
  *                       TMA gather4 row copies (cp.async.bulk.tensor.2d ... tile::gather4); 3-5 are bit-exact; 3 and 4
  *                       are slower, 5 is level with 2 at 14^3 and slower at 7^3: opt-in
- *   "car_bwd_variant"   0 = auto, 1 = direct scatter, 2 = plane-staged RED scatter, 3 = output-stationary (every
- *                       voxel stored once, no zero-fill, no atomics, deterministic; slower: opt-in)
+ *   "car_bwd_variant"   0 = auto (= 4), 1 = direct scatter, 2 = plane-staged RED scatter with per-thread-load staging,
+ *                       3 = output-stationary (every voxel stored once, no zero-fill, no atomics, deterministic;
+ *                       slower: opt-in), 4 = plane-staged RED scatter whose grads slices are staged by TMA tensor
+ *                       tile copies (falls back to 2 where the driver cannot encode the tensor map)
  *   "car_lanes_v"       0 = auto, 1 / 2 = float4 channel groups per thread in the plane / row-walk kernels
  *   "car_ctas_per_sm_target"   grid sizing of the plane kernels: depth-sample splits are chosen so that about this
  *                       many CTAs per SM exist (0 = default 16)
