@@ -32,7 +32,9 @@ EXPORTS = [
     "roi3d_version", "roi3d_strerror", "roi3d_last_cuda_error",
     "roi3d_nms3d_workspace_bytes", "roi3d_nms3d", "roi3d_nms3d_batched_workspace_bytes", "roi3d_nms3d_batched",
     "roi3d_car3d_fwd", "roi3d_car3d_grad_image", "roi3d_car3d_grad_boxes",
-    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_fwd_f16", "roi3d_pyramid_roi_align_grad", "roi3d_overlaps3d", "roi3d_decode_proposals",
+    "roi3d_car3d_workspace_bytes", "roi3d_car3d_fwd_ws", "roi3d_car3d_grad_image_ws",
+    "roi3d_pyramid_roi_align_fwd", "roi3d_pyramid_roi_align_fwd_f16", "roi3d_pyramid_roi_align_grad",
+    "roi3d_pyramid_roi_align_fwd_ws", "roi3d_pyramid_roi_align_fwd_f16_ws", "roi3d_pyramid_roi_align_grad_ws", "roi3d_overlaps3d", "roi3d_decode_proposals",
     "roi3d_topk_workspace_bytes", "roi3d_topk", "roi3d_gather_pad_boxes",
     "roi3d_proposal_layer_workspace_bytes", "roi3d_proposal_layer",
     "roi3d_refine_detections_workspace_bytes", "roi3d_refine_detections", "roi3d_mask_targets",
@@ -96,6 +98,12 @@ def _declare(lib):
     lib.roi3d_car3d_fwd.argtypes = [vp, i, i, i, i, i, vp, vp, i, i, i, i, i, f, vp, vp]
     lib.roi3d_car3d_grad_image.restype = i
     lib.roi3d_car3d_grad_image.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp, vp]
+    lib.roi3d_car3d_workspace_bytes.restype = sz
+    lib.roi3d_car3d_workspace_bytes.argtypes = [i]
+    lib.roi3d_car3d_fwd_ws.restype = i
+    lib.roi3d_car3d_fwd_ws.argtypes = [vp, i, i, i, i, i, vp, vp, i, i, i, i, i, f, vp, vp, sz, vp]
+    lib.roi3d_car3d_grad_image_ws.restype = i
+    lib.roi3d_car3d_grad_image_ws.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp, vp, sz, vp]
     lib.roi3d_car3d_grad_boxes.restype = i
     lib.roi3d_car3d_grad_boxes.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, i, i, i, vp, vp]
     lib.roi3d_pyramid_roi_align_fwd.restype = i
@@ -104,6 +112,12 @@ def _declare(lib):
     lib.roi3d_pyramid_roi_align_fwd_f16.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp]
     lib.roi3d_pyramid_roi_align_grad.restype = i
     lib.roi3d_pyramid_roi_align_grad.argtypes = [vp, vp, vp, i, i, vp, i, vp, i, i, i, vp]
+    lib.roi3d_pyramid_roi_align_fwd_ws.restype = i
+    lib.roi3d_pyramid_roi_align_fwd_ws.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp, sz, vp]
+    lib.roi3d_pyramid_roi_align_fwd_f16_ws.restype = i
+    lib.roi3d_pyramid_roi_align_fwd_f16_ws.argtypes = [vp, vp, i, i, vp, i, vp, i, i, i, vp, vp, sz, vp]
+    lib.roi3d_pyramid_roi_align_grad_ws.restype = i
+    lib.roi3d_pyramid_roi_align_grad_ws.argtypes = [vp, vp, vp, i, i, vp, i, vp, i, i, i, vp, sz, vp]
     lib.roi3d_overlaps3d.restype = i
     lib.roi3d_overlaps3d.argtypes = [vp, i, vp, i, vp, vp]
     lib.roi3d_decode_proposals.restype = i

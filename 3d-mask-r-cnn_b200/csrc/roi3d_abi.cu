@@ -138,10 +138,34 @@ int roi3d_nms3d(const float *boxes, const float *scores, int n, int max_out, flo
                         static_cast<cudaStream_t>(stream));
 }
 
+// ROI processing order (see car3d_order_kernel): worth its ~3 us kernel when a call moves enough bytes
+static const int *order_rois(const float *boxes, const int *box_index, int n, int rois_per_image, int pool_voxels, int C,
+                             void *workspace, size_t workspace_bytes, cudaStream_t s, int *rc)
+{
+    *rc = ROI3D_OK;
+    if (!workspace || workspace_bytes < roi3d_car3d_workspace_bytes(n) || (reinterpret_cast<uintptr_t>(workspace) & 3)) return nullptr;
+    if (option_value(OPT_EXPERIMENT) & 16) return nullptr;                 // A/B switch: ROIs in the order given
+    if (n < 32 || (long long)n * pool_voxels * C < (1ll << 26)) return nullptr;   // < 256 MB of crops: not worth a launch
+    int *perm = static_cast<int *>(workspace);
+    *rc = launch_car3d_order(boxes, box_index, n, rois_per_image, perm, s);
+    return *rc == ROI3D_OK ? perm : nullptr;
+}
+
+size_t roi3d_car3d_workspace_bytes(int n) { return n > 0 ? ((size_t)n * sizeof(int) + 255) & ~size_t(255) : 256; }
+
 int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
                     const float *boxes, const int *box_index, int n,
                     int ph, int pw, int pd, int method, float extrapolation_value,
                     float *crops, roi3d_stream_t stream)
+{
+    return roi3d_car3d_fwd_ws(image, B, H, W, D, C, boxes, box_index, n, ph, pw, pd, method, extrapolation_value, crops,
+                              nullptr, 0, stream);
+}
+
+int roi3d_car3d_fwd_ws(const float *image, int B, int H, int W, int D, int C,
+                       const float *boxes, const int *box_index, int n,
+                       int ph, int pw, int pd, int method, float extrapolation_value,
+                       float *crops, void *workspace, size_t workspace_bytes, roi3d_stream_t stream)
 {
     const CarGeom g{B, H, W, D, C, n, ph, pw, pd};
     if (!geom_ok(g)) return ROI3D_EINVAL;
@@ -172,13 +196,25 @@ int roi3d_car3d_fwd(const float *image, int B, int H, int W, int D, int C,
         if (rc != ROI3D_EUNSUPPORTED) return rc;
         variant = 2;
     }
-    if (variant == 2 && plane_ok) return launch_car3d_fwd_plane(image, boxes, box_index, g, extrapolation_value, crops, s);
+    if (variant == 2 && plane_ok) {
+        int rc;
+        const int *perm = order_rois(boxes, box_index, n, 0, ph * pw * pd, C, workspace, workspace_bytes, s, &rc);
+        if (rc != ROI3D_OK) return rc;
+        return launch_car3d_fwd_plane(image, boxes, box_index, g, extrapolation_value, crops, s, perm);
+    }
     return launch_car3d_fwd_direct(image, boxes, box_index, g, method, extrapolation_value, crops, s);
 }
 
 int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *box_ind, int n,
                            int ph, int pw, int pd, int B, int H, int W, int D, int C, int method,
                            float *grad_image, roi3d_stream_t stream)
+{
+    return roi3d_car3d_grad_image_ws(grads, boxes, box_ind, n, ph, pw, pd, B, H, W, D, C, method, grad_image, nullptr, 0, stream);
+}
+
+int roi3d_car3d_grad_image_ws(const float *grads, const float *boxes, const int *box_ind, int n,
+                              int ph, int pw, int pd, int B, int H, int W, int D, int C, int method,
+                              float *grad_image, void *workspace, size_t workspace_bytes, roi3d_stream_t stream)
 {
     const CarGeom g{B, H, W, D, C, n, ph, pw, pd};
     if (!geom_ok(g)) return ROI3D_EINVAL;
@@ -209,11 +245,17 @@ int roi3d_car3d_grad_image(const float *grads, const float *boxes, const int *bo
     if (!fused_fill) ROI3D_CUDA_TRY(cudaMemsetAsync(grad_image, 0, sizeof(float) * (size_t)B * H * W * D * C, s));
     if (n == 0) return ROI3D_OK;
     if (!grads || !boxes || !box_ind) return ROI3D_EINVAL;
+    const int *perm = nullptr;
+    if (plane) {                                         // the order kernel runs ahead of the zero-fill / scatter pair
+        int rc;
+        perm = order_rois(boxes, box_ind, n, 0, ph * pw * pd, C, workspace, workspace_bytes, s, &rc);
+        if (rc != ROI3D_OK) return rc;
+    }
     if (plane && tma) {
-        const int rc = launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill, true);
+        const int rc = launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill, true, perm);
         if (rc != ROI3D_EUNSUPPORTED) return rc;        // (nothing has been launched when the TMA build declines a shape)
     }
-    if (plane) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill);
+    if (plane) return launch_car3d_grad_image_plane(grads, boxes, box_ind, g, grad_image, s, fused_fill, false, perm);
     return launch_car3d_grad_image_direct(grads, boxes, box_ind, g, method, grad_image, s);
 }
 
@@ -406,7 +448,8 @@ static int pyramid_check(const int level_shapes[4][3], int B, int C, const float
 
 static int pyramid_fwd_any(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
                            const float *boxes, int rois_per_image, const float image_shape[3],
-                           int ph, int pw, int pd, void *pooled, bool half_out, roi3d_stream_t stream)
+                           int ph, int pw, int pd, void *pooled, bool half_out, void *workspace, size_t workspace_bytes,
+                           roi3d_stream_t stream)
 {
     const int rc = pyramid_check(level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd);
     if (rc != ROI3D_OK) return rc;
@@ -418,27 +461,57 @@ static int pyramid_fwd_any(const float *const feature_maps[4], const int level_s
         H[l] = level_shapes[l][0]; W[l] = level_shapes[l][1]; D[l] = level_shapes[l][2];
     }
     if (reinterpret_cast<uintptr_t>(pooled) & (half_out ? 7 : 15)) return ROI3D_EINVAL;
+    int orc;
+    const int *perm = order_rois(boxes, nullptr, B * rois_per_image, rois_per_image, ph * pw * pd, C, workspace, workspace_bytes,
+                                 static_cast<cudaStream_t>(stream), &orc);
+    if (orc != ROI3D_OK) return orc;
     return launch_pyramid_fwd(feature_maps, H, W, D, B, C, boxes, rois_per_image, image_shape[0], image_shape[1],
-                              image_shape[2], ph, pw, pd, pooled, half_out, static_cast<cudaStream_t>(stream));
+                              image_shape[2], ph, pw, pd, pooled, half_out, static_cast<cudaStream_t>(stream), perm);
 }
 
 int roi3d_pyramid_roi_align_fwd(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
                                 const float *boxes, int rois_per_image, const float image_shape[3],
                                 int ph, int pw, int pd, float *pooled, roi3d_stream_t stream)
 {
-    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled, false, stream);
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled, false, nullptr, 0, stream);
+}
+
+int roi3d_pyramid_roi_align_fwd_ws(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                   const float *boxes, int rois_per_image, const float image_shape[3],
+                                   int ph, int pw, int pd, float *pooled, void *workspace, size_t workspace_bytes,
+                                   roi3d_stream_t stream)
+{
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled, false,
+                           workspace, workspace_bytes, stream);
 }
 
 int roi3d_pyramid_roi_align_fwd_f16(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
                                     const float *boxes, int rois_per_image, const float image_shape[3],
                                     int ph, int pw, int pd, void *pooled_f16, roi3d_stream_t stream)
 {
-    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled_f16, true, stream);
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled_f16, true, nullptr, 0, stream);
+}
+
+int roi3d_pyramid_roi_align_fwd_f16_ws(const float *const feature_maps[4], const int level_shapes[4][3], int B, int C,
+                                       const float *boxes, int rois_per_image, const float image_shape[3],
+                                       int ph, int pw, int pd, void *pooled_f16, void *workspace, size_t workspace_bytes,
+                                       roi3d_stream_t stream)
+{
+    return pyramid_fwd_any(feature_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd, pooled_f16, true,
+                           workspace, workspace_bytes, stream);
 }
 
 int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], const int level_shapes[4][3], int B, int C,
                                  const float *boxes, int rois_per_image, const float image_shape[3],
                                  int ph, int pw, int pd, roi3d_stream_t stream)
+{
+    return roi3d_pyramid_roi_align_grad_ws(grads, grad_maps, level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd,
+                                           nullptr, 0, stream);
+}
+
+int roi3d_pyramid_roi_align_grad_ws(const float *grads, float *const grad_maps[4], const int level_shapes[4][3], int B, int C,
+                                    const float *boxes, int rois_per_image, const float image_shape[3],
+                                    int ph, int pw, int pd, void *workspace, size_t workspace_bytes, roi3d_stream_t stream)
 {
     const int rc = pyramid_check(level_shapes, B, C, boxes, rois_per_image, image_shape, ph, pw, pd);
     if (rc != ROI3D_OK) return rc;
@@ -450,8 +523,12 @@ int roi3d_pyramid_roi_align_grad(const float *grads, float *const grad_maps[4], 
         H[l] = level_shapes[l][0]; W[l] = level_shapes[l][1]; D[l] = level_shapes[l][2];
     }
     if (reinterpret_cast<uintptr_t>(grads) & 15) return ROI3D_EINVAL;
+    int orc = ROI3D_OK;
+    const int *perm = rois_per_image > 0 ? order_rois(boxes, nullptr, B * rois_per_image, rois_per_image, ph * pw * pd, C, workspace,
+                                                      workspace_bytes, static_cast<cudaStream_t>(stream), &orc) : nullptr;
+    if (orc != ROI3D_OK) return orc;
     return launch_pyramid_grad(grads, grad_maps, H, W, D, B, C, boxes, rois_per_image, image_shape[0], image_shape[1],
-                               image_shape[2], ph, pw, pd, static_cast<cudaStream_t>(stream));
+                               image_shape[2], ph, pw, pd, static_cast<cudaStream_t>(stream), perm);
 }
 
 }  // extern "C"

@@ -182,9 +182,11 @@ int launch_car3d_fwd_plane_tma(const float *image, const float *boxes, const int
 int launch_car3d_fwd_plane_g4(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                               float ext, float *crops, cudaStream_t stream);
 int launch_car3d_fwd_plane(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
-                           float ext, float *crops, cudaStream_t stream);
+                           float ext, float *crops, cudaStream_t stream, const int *perm = nullptr);
+int launch_car3d_order(const float *boxes, const int *box_index, int n, int rois_per_image, int *perm, cudaStream_t stream);
 int launch_car3d_grad_image_plane(const float *grads, const float *boxes, const int *box_ind, const CarGeom &g,
-                                  float *grad_image, cudaStream_t stream, bool zero_fill = false, bool tma = false);
+                                  float *grad_image, cudaStream_t stream, bool zero_fill = false, bool tma = false,
+                                  const int *perm = nullptr);
 struct PyrParams;
 int launch_car3d_fwd_sep(const float *image, const float *boxes, const int *box_index, const CarGeom &g,
                          float ext, void *crops, const PyrParams *pyr, bool half_out, cudaStream_t stream);
@@ -194,10 +196,10 @@ int launch_car3d_grad_image_os(const float *grads, const float *boxes, const int
                                float *grad_image, cudaStream_t stream);
 int launch_pyramid_fwd(const float *const images[4], const int H[4], const int W[4], const int D[4], int B, int C,
                        const float *boxes, int rois_per_image, float imH, float imW, float imD,
-                       int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream);
+                       int ph, int pw, int pd, void *crops, bool half_out, cudaStream_t stream, const int *perm = nullptr);
 int launch_pyramid_grad(const float *grads, float *const grad_images[4], const int H[4], const int W[4], const int D[4],
                         int B, int C, const float *boxes, int rois_per_image, float imH, float imW, float imD,
-                        int ph, int pw, int pd, cudaStream_t stream);
+                        int ph, int pw, int pd, cudaStream_t stream, const int *perm = nullptr);
 int launch_overlaps3d(const float *boxes1, int n, const float *boxes2, int m, float *out, cudaStream_t stream);
 int launch_decode_proposals(const float *anchors, const float *deltas, const int *index, int n, const float std_dev[6],
                             float image_depth, float *boxes, cudaStream_t stream);

@@ -354,13 +354,29 @@ def _crop_size(crop_size):
     return ph, pw, pd
 
 
+_car_ws_cache = {}
+
+
+def _car_workspace(n, device):
+    """Device scratch of the crop-and-resize calls (the ROI processing order, roi3d_car3d_workspace_bytes): one buffer
+    per (device, stream), grown on demand; calls on one stream are stream-ordered, so they can share it."""
+    nbytes = int(_lib.load().roi3d_car3d_workspace_bytes(int(n)))
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _car_ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _car_ws_cache[key] = buf
+    return buf
+
+
 def _fwd_device(image, boxes, box_index, crop, method, ext):
     B, H, W, D, C = image.shape
     n = boxes.shape[0]
     out = torch.empty((n,) + crop + (C,), dtype=torch.float32, device=image.device)
     lib = _lib.load()
-    _lib.check(lib.roi3d_car3d_fwd(_ptr(image), B, H, W, D, C, _ptr(boxes), _ptr(box_index), n,
-                                   crop[0], crop[1], crop[2], method, float(ext), _ptr(out), _stream_ptr()))
+    ws = _car_workspace(n, image.device)
+    _lib.check(lib.roi3d_car3d_fwd_ws(_ptr(image), B, H, W, D, C, _ptr(boxes), _ptr(box_index), n,
+                                      crop[0], crop[1], crop[2], method, float(ext), _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
     return out
 
 
@@ -369,8 +385,9 @@ def _grad_image_device(grads, boxes, box_ind, image_size, method):
     n, ph, pw, pd = grads.shape[:4]
     out = torch.empty((B, H, W, D, C), dtype=torch.float32, device=grads.device)
     lib = _lib.load()
-    _lib.check(lib.roi3d_car3d_grad_image(_ptr(grads), _ptr(boxes), _ptr(box_ind), n, ph, pw, pd,
-                                          B, H, W, D, C, method, _ptr(out), _stream_ptr()))
+    ws = _car_workspace(n, grads.device)
+    _lib.check(lib.roi3d_car3d_grad_image_ws(_ptr(grads), _ptr(boxes), _ptr(box_ind), n, ph, pw, pd,
+                                             B, H, W, D, C, method, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
     return out
 
 
@@ -508,8 +525,9 @@ class PyramidROIAlign3DFunction(torch.autograd.Function):
         C = fms[0].shape[4]
         out = torch.empty((B, R) + tuple(pool_shape) + (C,), dtype=torch.float32, device=boxes.device)
         ptrs, shapes, ishape = _pyr_args(fms, image_shape)
-        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd(ptrs, shapes, B, C, _ptr(boxes), R, ishape, pool_shape[0],
-                                                           pool_shape[1], pool_shape[2], _ptr(out), _stream_ptr()))
+        ws = _car_workspace(B * R, boxes.device)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd_ws(ptrs, shapes, B, C, _ptr(boxes), R, ishape, pool_shape[0],
+                                                              pool_shape[1], pool_shape[2], _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
         ctx.save_for_backward(boxes)
         ctx.meta = (tuple(image_shape), tuple(pool_shape), [tuple(t.shape) for t in fms])
         return out
@@ -522,8 +540,9 @@ class PyramidROIAlign3DFunction(torch.autograd.Function):
         B, R = boxes.shape[:2]
         gms = [torch.empty(sh, dtype=torch.float32, device=grad.device) for sh in shapes]
         ptrs, cshapes, ishape = _pyr_args(gms, image_shape)
-        _lib.check(_lib.load().roi3d_pyramid_roi_align_grad(_ptr(grad), ptrs, cshapes, B, shapes[0][4], _ptr(boxes), R, ishape,
-                                                            pool_shape[0], pool_shape[1], pool_shape[2], _stream_ptr()))
+        ws = _car_workspace(B * R, grad.device)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_grad_ws(_ptr(grad), ptrs, cshapes, B, shapes[0][4], _ptr(boxes), R, ishape,
+                                                               pool_shape[0], pool_shape[1], pool_shape[2], _ptr(ws), ws.numel(), _stream_ptr()))
         return (None, None, None) + tuple(gms)
 
 
@@ -549,8 +568,9 @@ def pyramid_roi_align_3d(boxes, image_shape, feature_maps, pool_shape, out_dtype
         ps = tuple(int(v) for v in pool_shape)
         out = torch.empty((B, R) + ps + (C,), dtype=torch.float16, device=dev)
         ptrs, shapes, ishape = _pyr_args(fms, image_shape)
-        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd_f16(ptrs, shapes, B, C, _ptr(boxes), R, ishape, ps[0], ps[1], ps[2],
-                                                               _ptr(out), _stream_ptr()))
+        ws = _car_workspace(B * R, dev)
+        _lib.check(_lib.load().roi3d_pyramid_roi_align_fwd_f16_ws(ptrs, shapes, B, C, _ptr(boxes), R, ishape, ps[0], ps[1], ps[2],
+                                                                  _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
         return out
     _require(out_dtype == torch.float32, "out_dtype must be float32 or float16")
     return PyramidROIAlign3DFunction.apply(boxes, tuple(image_shape), tuple(int(v) for v in pool_shape), *feature_maps)

@@ -76,12 +76,15 @@ def run_cfg4(torch, rb, lib, dev, world, peak, ptr, stream, barrier):
     B, H, W, D, C = shape
     fb = roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=False)
     bb = roi3d_synth.car_algorithmic_bytes(boxes, shape, crop, backward=True)
+    car_ws = torch.empty(int(lib.roi3d_car3d_workspace_bytes(n)), dtype=torch.uint8, device=dev)   # caller-owned scratch (ROI order)
 
     def fwd():
-        rb._lib.check(lib.roi3d_car3d_fwd(ptr(image), B, H, W, D, C, ptr(tb), ptr(ti), n, 14, 14, 14, 0, 0.0, ptr(crops), stream()))
+        rb._lib.check(lib.roi3d_car3d_fwd_ws(ptr(image), B, H, W, D, C, ptr(tb), ptr(ti), n, 14, 14, 14, 0, 0.0, ptr(crops),
+                                             ptr(car_ws), car_ws.numel(), stream()))
 
     def bwd():
-        rb._lib.check(lib.roi3d_car3d_grad_image(ptr(grads), ptr(tb), ptr(ti), n, 14, 14, 14, B, H, W, D, C, 0, ptr(gimg), stream()))
+        rb._lib.check(lib.roi3d_car3d_grad_image_ws(ptr(grads), ptr(tb), ptr(ti), n, 14, 14, 14, B, H, W, D, C, 0, ptr(gimg),
+                                                    ptr(car_ws), car_ws.numel(), stream()))
 
     def ev_time(fn, reps):
         for _ in range(3):
@@ -114,6 +117,7 @@ def run_mixed_levels(torch, rb, lib, dev, images, ptr, stream):
     the fused entry points.  Both legs are CUDA-graph replays of forward + backward for the 7^3 and 14^3 pools."""
     vp = ctypes.c_void_p
     R = ROIS_PER_IMAGE
+    car_ws = torch.empty(int(lib.roi3d_car3d_workspace_bytes(BATCH * R)), dtype=torch.uint8, device=dev)
     boxes_br = np.stack([roi3d_synth.rois(R, VOLUME, 7000 + b, side_px=(32.0, 128.0)) for b in range(BATCH)])
     flat = boxes_br.reshape(-1, 6)
     bidx_all = np.repeat(np.arange(BATCH, dtype=np.int32), R)
@@ -141,8 +145,8 @@ def run_mixed_levels(torch, rb, lib, dev, images, ptr, stream):
             for pl in per_level:
                 B_, H, W, D, _ = pl["fm"].shape
                 out = crops_lv[c][off:off + pl["n"]]
-                rb._lib.check(lib.roi3d_car3d_fwd(ptr(pl["fm"]), B_, H, W, D, C, ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"],
-                                                  c[0], c[1], c[2], 0, 0.0, vp(out.data_ptr()), stream()))
+                rb._lib.check(lib.roi3d_car3d_fwd_ws(ptr(pl["fm"]), B_, H, W, D, C, ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"],
+                                                     c[0], c[1], c[2], 0, 0.0, vp(out.data_ptr()), ptr(car_ws), car_ws.numel(), stream()))
                 off += pl["n"]
             if glue:
                 torch.index_select(crops_lv[c], 0, order, out=pooled[c])        # tf.gather(pooled, ix), core/models.py:675-683
@@ -154,8 +158,8 @@ def run_mixed_levels(torch, rb, lib, dev, images, ptr, stream):
             for pl in per_level:
                 B_, H, W, D, _ = pl["fm"].shape
                 gin = src[off:off + pl["n"]]
-                rb._lib.check(lib.roi3d_car3d_grad_image(vp(gin.data_ptr()), ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"], c[0], c[1], c[2],
-                                                         B_, H, W, D, C, 0, ptr(pl["gimg"][c]), stream()))
+                rb._lib.check(lib.roi3d_car3d_grad_image_ws(vp(gin.data_ptr()), ptr(pl["boxes"]), ptr(pl["bidx"]), pl["n"], c[0], c[1], c[2],
+                                                            B_, H, W, D, C, 0, ptr(pl["gimg"][c]), ptr(car_ws), car_ws.numel(), stream()))
                 off += pl["n"]
 
     lshapes = (ctypes.c_int * 12)(*[int(d) for fm in fms for d in fm.shape[1:4]])
@@ -165,11 +169,11 @@ def run_mixed_levels(torch, rb, lib, dev, images, ptr, stream):
 
     def fused_step():
         for c in CROPS:
-            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), R, ishape, c[0], c[1], c[2],
-                                                          ptr(pooled[c]), stream()))
+            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd_ws(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), R, ishape, c[0], c[1], c[2],
+                                                             ptr(pooled[c]), ptr(car_ws), car_ws.numel(), stream()))
         for c in CROPS:
-            rb._lib.check(lib.roi3d_pyramid_roi_align_grad(ptr(grads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br), R, ishape,
-                                                           c[0], c[1], c[2], stream()))
+            rb._lib.check(lib.roi3d_pyramid_roi_align_grad_ws(ptr(grads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br), R, ishape,
+                                                              c[0], c[1], c[2], ptr(car_ws), car_ws.numel(), stream()))
 
     def graph_ms(fn, reps=20):
         for _ in range(2):
@@ -291,6 +295,8 @@ def run_ours(args):
     lib = rb._lib.load()
     vp = ctypes.c_void_p
     stream = lambda: vp(torch.cuda.current_stream().cuda_stream)   # noqa: E731
+    if os.environ.get("BENCH_CAR_EXPERIMENT"):                     # A/B switches of profiles/*.py (e.g. 16: ROIs in the order given)
+        rb.set_option("car_experiment", int(os.environ["BENCH_CAR_EXPERIMENT"]))
 
     ops = make_workload(seed=2002)         # weak scaling: every rank runs the SAME batch, so per-GPU work is fixed exactly
     seed_is_default = True                 # (the ncu traffic figures were captured on this ROI set)
@@ -311,17 +317,22 @@ def run_ours(args):
     def ptr(t):
         return vp(t.data_ptr() if t.numel() else 0)
 
+    # caller-owned scratch of the crop-and-resize calls (the ROI processing order), one per op node (nodes may run on
+    # different streams with --op-streams)
+    for op in ops:
+        op["d_ws"] = torch.empty(int(lib.roi3d_car3d_workspace_bytes(max(op["n"], 1))), dtype=torch.uint8, device=dev)
+
     def fwd(op):
         B, H, W, D, C = op["shape"]
         c = op["crop"]
-        rb._lib.check(lib.roi3d_car3d_fwd(ptr(op["d_image"]), B, H, W, D, C, ptr(op["d_boxes"]), ptr(op["d_bidx"]),
-                                          op["n"], c[0], c[1], c[2], 0, 0.0, ptr(op["d_crops"]), stream()))
+        rb._lib.check(lib.roi3d_car3d_fwd_ws(ptr(op["d_image"]), B, H, W, D, C, ptr(op["d_boxes"]), ptr(op["d_bidx"]),
+                                             op["n"], c[0], c[1], c[2], 0, 0.0, ptr(op["d_crops"]), ptr(op["d_ws"]), op["d_ws"].numel(), stream()))
 
     def bwd(op):
         B, H, W, D, C = op["shape"]
         c = op["crop"]
-        rb._lib.check(lib.roi3d_car3d_grad_image(ptr(op["d_grads"]), ptr(op["d_boxes"]), ptr(op["d_bidx"]), op["n"],
-                                                 c[0], c[1], c[2], B, H, W, D, C, 0, ptr(op["d_gimg"]), stream()))
+        rb._lib.check(lib.roi3d_car3d_grad_image_ws(ptr(op["d_grads"]), ptr(op["d_boxes"]), ptr(op["d_bidx"]), op["n"],
+                                                    c[0], c[1], c[2], B, H, W, D, C, 0, ptr(op["d_gimg"]), ptr(op["d_ws"]), op["d_ws"].numel(), stream()))
 
     # The 8 forward nodes of a step are independent of each other, and so are the 8 grad-image nodes (each writes its
     # own tensor; TF's executor schedules such nodes concurrently, SURVEY.md 8b "Threading / streams").  With
@@ -459,13 +470,15 @@ def run_ours(args):
     gms = {c: [torch.empty_like(fm) for fm in fms] for c in CROPS}
     gm_ptrs = {c: (vp * 4)(*[g.data_ptr() for g in gms[c]]) for c in CROPS}
 
+    pyr_ws = torch.empty(int(lib.roi3d_car3d_workspace_bytes(BATCH * ROIS_PER_IMAGE)), dtype=torch.uint8, device=dev)
+
     def fused_step():
         for c in CROPS:
-            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), ROIS_PER_IMAGE, ishape,
-                                                          c[0], c[1], c[2], ptr(pooled[c]), stream()))
+            rb._lib.check(lib.roi3d_pyramid_roi_align_fwd_ws(fm_ptrs, lshapes, BATCH, C, ptr(d_boxes_br), ROIS_PER_IMAGE, ishape,
+                                                             c[0], c[1], c[2], ptr(pooled[c]), ptr(pyr_ws), pyr_ws.numel(), stream()))
         for c in CROPS:
-            rb._lib.check(lib.roi3d_pyramid_roi_align_grad(ptr(pgrads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br),
-                                                           ROIS_PER_IMAGE, ishape, c[0], c[1], c[2], stream()))
+            rb._lib.check(lib.roi3d_pyramid_roi_align_grad_ws(ptr(pgrads[c]), gm_ptrs[c], lshapes, BATCH, C, ptr(d_boxes_br),
+                                                              ROIS_PER_IMAGE, ishape, c[0], c[1], c[2], ptr(pyr_ws), pyr_ws.numel(), stream()))
 
     for _ in range(3):
         fused_step()

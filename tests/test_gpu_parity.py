@@ -306,6 +306,34 @@ def test_car_empty_and_single(rb, cuda_device):
     assert isinstance(hz, np.ndarray) and hz.shape == (2, 4, 4, 4, 8) and hz.dtype == np.float32 and not hz.any()
 
 
+def test_roi_processing_order_does_not_change_results(rb, cuda_device):
+    """The workspace entry points process the ROIs sorted by (image, y centre): the forward is bit-identical to the plain
+    entry point and to the oracle, the backward stays within 1e-4; an undersized workspace falls back to the given order."""
+    import ctypes
+    import torch
+    lib = rb._lib.load()
+    vp = ctypes.c_void_p
+    B, H, W, D, C, n, crop = 3, 16, 16, 24, 256, 96, (14, 14, 14)     # 96 x 2744 x 256 floats: above the ordering threshold
+    image, boxes, bidx, grads = car_inputs(5150, B, H, W, D, C, n, crop)
+    bidx = np.random.default_rng(1).integers(0, B, n).astype(np.int32)            # images interleaved
+    t_img, t_b, t_i, t_g = (dev(x, cuda_device) for x in (image, boxes, bidx, grads))
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    ref = oracle.crop_and_resize_3d(image, boxes, bidx, crop, threads=max(1, oracle.max_threads()))
+    gref = oracle.crop_and_resize_3d_grad_image(grads, boxes, bidx, image.shape, threads=max(1, oracle.max_threads()))
+    full = int(lib.roi3d_car3d_workspace_bytes(n))
+    assert full >= 4 * n and int(lib.roi3d_car3d_workspace_bytes(0)) > 0
+    for nbytes in (full, 8, 0):
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=cuda_device)
+        out = torch.empty((n,) + crop + (C,), device=cuda_device)
+        rb._lib.check(lib.roi3d_car3d_fwd_ws(vp(t_img.data_ptr()), B, H, W, D, C, vp(t_b.data_ptr()), vp(t_i.data_ptr()), n, *crop, 0, 0.0,
+                                             vp(out.data_ptr()), vp(ws.data_ptr()) if nbytes else None, nbytes, stream))
+        assert np.array_equal(out.cpu().numpy(), ref), nbytes
+        gi = torch.empty(image.shape, device=cuda_device)
+        rb._lib.check(lib.roi3d_car3d_grad_image_ws(vp(t_g.data_ptr()), vp(t_b.data_ptr()), vp(t_i.data_ptr()), n, *crop, B, H, W, D, C, 0,
+                                                    vp(gi.data_ptr()), vp(ws.data_ptr()) if nbytes else None, nbytes, stream))
+        assert rel_ok(gi.cpu().numpy(), gref, BWD_TOL), nbytes
+
+
 @pytest.mark.parametrize("uploads_first", [False, True])
 def test_host_buffer_pipeline_policies(rb, cuda_device, uploads_first):
     """Host buffers in, host results out, several independent ops inside one `deferred` block: both copy policies
