@@ -702,6 +702,22 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
 }
+// the same with an L2 eviction-priority hint: grads are read exactly once, so they should be the first lines to leave L2 --
+// what must stay there are the grad-image lines the REDs keep hitting
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mbar,
+                                                 unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d_hint(const CUtensorMap *map, int c0, int c1, int c2, unsigned long long pol) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3}], %4;"
+                 :: "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                  :: "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -850,8 +866,14 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
                 if (threadIdx.x == 0) {
                     fence_proxy_async();                       // the previous slice's generic reads (before the barrier) are done
                     mbar_expect_tx(mbar, (unsigned)L.zcap * ebytes);
-                    tma_load_3d(smem_u32(Graw), &tmap, chunk * cl * V * 4, k, (b * g.ph + ya) * g.pw, mbar);
-                    if (k + 1 < k1) tma_prefetch_3d(&tmap, chunk * cl * V * 4, k + 1, (b * g.ph + ya) * g.pw);
+                    if (only_image == -2) {                    // A/B (car_experiment bit 32): no eviction hint
+                        tma_load_3d(smem_u32(Graw), &tmap, chunk * cl * V * 4, k, (b * g.ph + ya) * g.pw, mbar);
+                        if (k + 1 < k1) tma_prefetch_3d(&tmap, chunk * cl * V * 4, k + 1, (b * g.ph + ya) * g.pw);
+                    } else {
+                        const unsigned long long pol = l2_evict_first_policy();
+                        tma_load_3d_hint(smem_u32(Graw), &tmap, chunk * cl * V * 4, k, (b * g.ph + ya) * g.pw, mbar, pol);
+                        if (k + 1 < k1) tma_prefetch_3d_hint(&tmap, chunk * cl * V * 4, k + 1, (b * g.ph + ya) * g.pw, pol);
+                    }
                 }
                 mbar_wait_bounded(mbar, tma_parity);           // every thread sees the landed slice
                 tma_parity ^= 1u;
@@ -1253,6 +1275,7 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
         ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
+    const int nohint = (option_value(OPT_EXPERIMENT) & 32) ? -2 : -1;      // only_image < 0: all images (-2: A/B, no L2 hint)
     if (zero_fill) {
         // Opt-in experiment ("car_bwd_image_split" = 1): zero-fill and scatter image by image, so that the REDs find the zeros
         // still in L2 instead of fetching them back from DRAM.  Measured at cfg2 (profiles/split_experiment.py): 0.438 vs
@@ -1265,14 +1288,14 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
             zero_fill_kernel<<<fill_grid(), 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
             ROI3D_LAUNCH_CHECK();
             ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
-                                            grad_image, PyrParams{}, split ? img : -1, tmap));
+                                            grad_image, PyrParams{}, split ? img : nohint, tmap));
             if (img + 1 < (split ? g.B : 1)) ROI3D_LAUNCH_CHECK();
         }
     } else if (pdl_after_fill) {                               // the caller has just enqueued the zero-fill kernel
         ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
-                                        grad_image, pyr ? *pyr : PyrParams{}, -1, tmap));
+                                        grad_image, pyr ? *pyr : PyrParams{}, nohint, tmap));
     } else {
-        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, -1, tmap);
+        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, nohint, tmap);
     }
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;

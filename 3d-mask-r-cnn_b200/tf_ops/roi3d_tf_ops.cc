@@ -190,9 +190,13 @@ class CropAndResize3DGpuOp : public tf::OpKernel {
     tf::Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({n, ph, pw, pd, C}), &out));
     if (n == 0) return;
-    const int rc = roi3d_car3d_fwd(image.flat<float>().data(), B, H, W, D, C, boxes.flat<float>().data(),
-                                   box_index.flat<int32_t>().data(), n, ph, pw, pd, method_, extrapolation_value_,
-                                   out->flat<float>().data(), tf::GetGpuStream(ctx));
+    // scratch for the ROI processing order (include/roi3d.h: the *_ws entry points); a temp of the op, like NMS's workspace
+    tf::Tensor ws;
+    const size_t ws_bytes = roi3d_car3d_workspace_bytes(n);
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_INT32, tf::TensorShape({static_cast<int64_t>(ws_bytes / 4)}), &ws));
+    const int rc = roi3d_car3d_fwd_ws(image.flat<float>().data(), B, H, W, D, C, boxes.flat<float>().data(),
+                                      box_index.flat<int32_t>().data(), n, ph, pw, pd, method_, extrapolation_value_,
+                                      out->flat<float>().data(), ws.flat<int32_t>().data(), ws_bytes, tf::GetGpuStream(ctx));
     OP_REQUIRES_OK(ctx, Roi3dStatus(rc, "CropAndResize3D"));
   }
  private:
@@ -231,9 +235,12 @@ class CropAndResize3DGradImageGpuOp : public tf::OpKernel {
     OP_REQUIRES(ctx, grads.dim_size(4) == C, tf::errors::InvalidArgument("image_size and grads are incompatible"));
     tf::Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, H, W, D, C}), &out));
-    const int rc = roi3d_car3d_grad_image(grads.flat<float>().data(), boxes.flat<float>().data(),
-                                          box_index.flat<int32_t>().data(), n, ph, pw, pd, B, H, W, D, C, method_,
-                                          out->flat<float>().data(), tf::GetGpuStream(ctx));
+    tf::Tensor ws;
+    const size_t ws_bytes = roi3d_car3d_workspace_bytes(n);
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_INT32, tf::TensorShape({static_cast<int64_t>(ws_bytes / 4)}), &ws));
+    const int rc = roi3d_car3d_grad_image_ws(grads.flat<float>().data(), boxes.flat<float>().data(),
+                                             box_index.flat<int32_t>().data(), n, ph, pw, pd, B, H, W, D, C, method_,
+                                             out->flat<float>().data(), ws.flat<int32_t>().data(), ws_bytes, tf::GetGpuStream(ctx));
     OP_REQUIRES_OK(ctx, Roi3dStatus(rc, "CropAndResize3DGradImage"));
   }
  private:
