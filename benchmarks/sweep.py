@@ -71,8 +71,9 @@ def main():
                     grads = torch.randn((n, p, p, p, C), device=dev)
                     B, H, W, D, _ = shape
                     s = lambda: vp(torch.cuda.current_stream().cuda_stream)   # noqa: E731
-                    f = lambda: rb._lib.check(lib.roi3d_car3d_fwd(vp(image.data_ptr()), B, H, W, D, C, vp(tb.data_ptr()), vp(ti.data_ptr()), n, p, p, p, 0, 0.0, vp(crops.data_ptr()), s()))   # noqa: E731
-                    g = lambda: rb._lib.check(lib.roi3d_car3d_grad_image(vp(grads.data_ptr()), vp(tb.data_ptr()), vp(ti.data_ptr()), n, p, p, p, B, H, W, D, C, 0, vp(gimg.data_ptr()), s()))   # noqa: E731
+                    ws = torch.empty(int(lib.roi3d_car3d_workspace_bytes(n)), dtype=torch.uint8, device=dev)   # caller-owned scratch (ROI order)
+                    f = lambda: rb._lib.check(lib.roi3d_car3d_fwd_ws(vp(image.data_ptr()), B, H, W, D, C, vp(tb.data_ptr()), vp(ti.data_ptr()), n, p, p, p, 0, 0.0, vp(crops.data_ptr()), vp(ws.data_ptr()), ws.numel(), s()))   # noqa: E731
+                    g = lambda: rb._lib.check(lib.roi3d_car3d_grad_image_ws(vp(grads.data_ptr()), vp(tb.data_ptr()), vp(ti.data_ptr()), n, p, p, p, B, H, W, D, C, 0, vp(gimg.data_ptr()), vp(ws.data_ptr()), ws.numel(), s()))   # noqa: E731
                     tf_, tb_ = timeit(f, args.reps), timeit(g, args.reps)
                     fb = roi3d_synth.car_algorithmic_bytes(boxes, shape, (p, p, p), False)
                     bb = roi3d_synth.car_algorithmic_bytes(boxes, shape, (p, p, p), True)
