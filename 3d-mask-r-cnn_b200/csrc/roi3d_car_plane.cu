@@ -80,13 +80,15 @@ __device__ __forceinline__ void build_axis_tables(PlaneShared &S, const CarGeom 
     }
     __syncthreads();
     {   // dedupe: candidate j is a "first" if no earlier candidate has its value; list = firsts in order
-        const int a = tid / (2 * PL_MAXP), j = tid % (2 * PL_MAXP);
+        const bool act = tid < 4 * PL_MAXP;                   // (CTAs of more than 256 threads: the other warps only join the barriers)
+        const int a = act ? tid / (2 * PL_MAXP) : 0, j = tid % (2 * PL_MAXP);
         const int p = a ? g.pw : g.ph;
         AxisTab &T = S.ax[a];
         const int v = T.cand[j];
         const bool fast = 2 * p <= 32;                        // the axis' candidates fit one warp (crops up to 16)
         int fo = j;
-        if (fast) {
+        if (!act) {
+        } else if (fast) {
             if (j < 32) {                                      // warp 0 (y) / warp 4 (x): match instead of searching
                 const bool valid = j < 2 * p && v >= 0;
                 const unsigned m = __match_any_sync(0xffffffffu, valid ? v : -1 - j);
@@ -108,7 +110,7 @@ __device__ __forceinline__ void build_axis_tables(PlaneShared &S, const CarGeom 
             T.first[j] = (j < 2 * p && v >= 0 && fo == j) ? 1 : 0;
         }
         __syncthreads();
-        if (!fast) {
+        if (act && !fast) {
             if (j < 2 * p) {
                 int pos = -1;
                 if (v >= 0) {
@@ -184,8 +186,9 @@ struct __align__(16) OutEntry {             // per output (y, x) of the current 
 // ---------------------------------------------------------------------------------
 // FULL: every channel lane of every chunk carries live channels ((C / 4) % (cl * V) == 0, e.g. C = 256): the per-group
 // predicates, and the divergence bookkeeping (BSSY / BSYNC) they drag into every inner loop, compile away.
-template <int V, bool PYR, bool HALF = false, bool FULL = false>
-__global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
+// NT: threads per CTA (256; 512 = experiment: 32 voxel / output slots per pass instead of 16, two CTAs per SM)
+template <int V, bool PYR, bool HALF = false, bool FULL = false, int NT = PL_THREADS>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : ((V == 1) ? 4 : 3))
 car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
                        const int *__restrict__ box_index, CarGeom g, PlaneLaunch L, float ext,
                        void *__restrict__ crops, const PyrParams P)
@@ -230,7 +233,7 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
     const AxisTab &Y = S.ax[0], &X = S.ax[1];
     const int nx = X.n;
     const int cl = L.cl;
-    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
+    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = NT / cl;
     const int c4 = chunk * cl * V + lane;                   // first float4 channel group of this thread
     bool von[V];
 #pragma unroll
@@ -257,12 +260,12 @@ car3d_fwd_plane_kernel(const float *__restrict__ image, const float *__restrict_
         const int nvox = (r1 >= r0) ? (r1 - r0 + 1) * nx : 0;
         const int nout = (yb - ya) * g.pw;
         // ---- per-tile tables ----------------------------------------------------------
-        for (int idx = threadIdx.x; idx < nvox; idx += PL_THREADS) {
+        for (int idx = threadIdx.x; idx < nvox; idx += NT) {
             const int r = idx / nx, cx = idx - r * nx;
             voff[idx] = (unsigned)Y.list[r0 + r] * sH + (unsigned)X.list[cx] * sW;
         }
         int my_bad = 0;
-        for (int idx = threadIdx.x; idx < nout; idx += PL_THREADS) {
+        for (int idx = threadIdx.x; idx < nout; idx += NT) {
             const int yy = idx / g.pw, x = idx - yy * g.pw, y = ya + yy;
             const int py0 = Y.pos0[y], px0 = X.pos0[x];
             OutEntry e;
@@ -768,8 +771,8 @@ __device__ __forceinline__ void build_lists(const PlaneShared &S, BwdLists &B, c
 // TMA: the k-slice of grads is staged by ONE tensor tile copy (cp.async.bulk.tensor.3d, box = channel chunk x 1 depth
 // sample x zcap (y, x) samples) issued by one thread and awaited on an mbarrier, instead of 2-3 dependent batches of
 // per-thread loads + shared stores; the next slice is pulled towards L2 by one tensor prefetch instruction.
-template <int V, bool PYR, bool FULL = false, bool TMA = false>
-__global__ void __launch_bounds__(PL_THREADS, (V == 1) ? 4 : 3)
+template <int V, bool PYR, bool FULL = false, bool TMA = false, int NT = PL_THREADS>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : ((V == 1) ? 4 : 3))
 car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__restrict__ boxes,
                               const int *__restrict__ box_ind, CarGeom g, PlaneLaunch L,
                               float *__restrict__ grad_image, const PyrParams P, const int only_image,
@@ -821,7 +824,7 @@ car3d_grad_image_plane_kernel(const float *__restrict__ grads, const float *__re
 
     const int nx = X.n, ny = Y.n;
     if (nx == 0 || ny == 0) return;                           // no in-range sample: nothing to scatter
-    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = PL_THREADS / cl;
+    const int lane = threadIdx.x % cl, slot = threadIdx.x / cl, vs = NT / cl;
     const int c4 = chunk * cl * V + lane;
     bool von[V];
 #pragma unroll
@@ -1075,11 +1078,21 @@ static int launch_fwd_plane_impl(const float *image, const float *boxes, const i
     else        kern = half_out ? (full ? (K)car3d_fwd_plane_kernel<1, true, true, true> : (K)car3d_fwd_plane_kernel<1, true, true, false>)
                      : pyr      ? (full ? (K)car3d_fwd_plane_kernel<1, true, false, true> : (K)car3d_fwd_plane_kernel<1, true, false, false>)
                                 : (full ? (K)car3d_fwd_plane_kernel<1, false, false, true> : (K)car3d_fwd_plane_kernel<1, false, false, false>);
+    // 512-thread CTAs (32 voxel / output slots per pass, two CTAs per SM at 64 registers) for crops of 12 x 12 outputs per
+    // depth slice and more: fewer dependent passes per stage -- cfg2 14^3 0.246 -> 0.234 ms, 28^3 0.339 -> 0.31 ms, 7^3
+    // slower (profiles/fwd_threads_ab.py; car_experiment bit 128 keeps 256 threads)
+    int nthreads = PL_THREADS;
+    if (V == 2 && full && g.ph * g.pw >= 144 && !(option_value(OPT_EXPERIMENT) & 128)) {
+        kern = half_out ? (K)car3d_fwd_plane_kernel<2, true, true, true, 512>
+             : pyr      ? (K)car3d_fwd_plane_kernel<2, true, false, true, 512>
+                        : (K)car3d_fwd_plane_kernel<2, false, false, true, 512>;
+        nthreads = 512;
+    }
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
     if (grid > 0x7fffffffll) return ROI3D_EUNSUPPORTED;
-    kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, pyr ? *pyr : PyrParams{});
+    kern<<<(unsigned)grid, nthreads, smem, stream>>>(image, boxes, box_index, g, L, ext, crops, pyr ? *pyr : PyrParams{});
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
 }
@@ -1271,6 +1284,11 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
                            : (full ? (K)car3d_grad_image_plane_kernel<2, false, true> : (K)car3d_grad_image_plane_kernel<2, false, false>);
     else        kern = pyr ? (full ? (K)car3d_grad_image_plane_kernel<1, true, true> : (K)car3d_grad_image_plane_kernel<1, true, false>)
                            : (full ? (K)car3d_grad_image_plane_kernel<1, false, true> : (K)car3d_grad_image_plane_kernel<1, false, false>);
+    int nthreads = PL_THREADS;
+    if ((option_value(OPT_EXPERIMENT) & 256) && tma && V == 2 && full) {            // A/B: 512-thread CTAs
+        kern = pyr ? (K)car3d_grad_image_plane_kernel<2, true, true, true, 512> : (K)car3d_grad_image_plane_kernel<2, false, true, true, 512>;
+        nthreads = 512;
+    }
     if (smem > 48 * 1024)
         ROI3D_CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     const long long grid = (long long)g.n * L.ksplits * L.chunks;
@@ -1287,15 +1305,15 @@ static int launch_grad_plane_impl(const float *grads, const float *boxes, const 
             float *dst = grad_image + (split ? (size_t)img * (per_image / 4) : 0);
             zero_fill_kernel<<<fill_grid(), 256, 0, stream>>>(reinterpret_cast<float4 *>(dst), n4);
             ROI3D_LAUNCH_CHECK();
-            ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
+            ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(nthreads), smem, stream, true, grads, boxes, box_ind, g, L,
                                             grad_image, PyrParams{}, split ? img : nohint, tmap));
             if (img + 1 < (split ? g.B : 1)) ROI3D_LAUNCH_CHECK();
         }
     } else if (pdl_after_fill) {                               // the caller has just enqueued the zero-fill kernel
-        ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(PL_THREADS), smem, stream, true, grads, boxes, box_ind, g, L,
+        ROI3D_CUDA_TRY(launch_dependent(kern, dim3((unsigned)grid), dim3(nthreads), smem, stream, true, grads, boxes, box_ind, g, L,
                                         grad_image, pyr ? *pyr : PyrParams{}, nohint, tmap));
     } else {
-        kern<<<(unsigned)grid, PL_THREADS, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, nohint, tmap);
+        kern<<<(unsigned)grid, nthreads, smem, stream>>>(grads, boxes, box_ind, g, L, grad_image, pyr ? *pyr : PyrParams{}, nohint, tmap);
     }
     ROI3D_LAUNCH_CHECK();
     return ROI3D_OK;
